@@ -1,0 +1,141 @@
+/*
+ * odam_sq.h -- C ABI of the B200-native multi-view superquadric optimiser.
+ *
+ * This is the drop-in boundary for ONE path of likojack/ODAM: the per-track optimisation that
+ *   src/scripts/run_multi_view.py:56-67   (SuperQuadricOptimizer(...); .run(bbox_lines, None, P_cws, n_iters);
+ *                                          Q_est.compute_ellipsoid_points(use_numpy=True))
+ * performs object by object on the CPU, i.e.
+ *   src/super_quadric/sq_libs.py:432-475  SuperQuadricOptimizer.run            -> odam_sq_optimize[_host]
+ *   src/super_quadric/sq_libs.py:577-595  SuperQuadric.compute_ellipsoid_points -> odam_sq_sample_points[_host]
+ *   src/super_quadric/sq_libs.py:547-554  SuperQuadric.get_bbox                -> odam_sq_project_boxes[_host]
+ *   src/super_quadric/learnable_primitives/fast_sampler/sampling.hpp:5-15 sample_on_batch (the reference's
+ *   own native entry point, bound by _sampler.pyx:413-454) is subsumed: the sampler runs inside the kernels.
+ *
+ * Everything is plain pointers and sizes; no C++/torch types.  All objects of a call are optimised
+ * in ONE persistent kernel launch (one CTA per object, all iterations on chip).
+ *
+ * Layouts (all little-endian, densely packed, row-major)
+ *   params  [n][9]  float   translate x,y,z | yaw angle | scales s1,s2,s3 (= sqrt(dim/2), sq_libs.py:361)
+ *                           | shape logits h1,h2 (e = 0.2 + 1.4*sigmoid(h), sq_libs.py:26-27)
+ *   cls     [n]     int32   class id 0..7 (sq_libs.py:13-22), only read when a prior is given
+ *   view_off[n+1]   int32   CSR offsets into the per-view arrays; object i owns views view_off[i]..view_off[i+1]-1
+ *   Ms      [SV][12] float  P_cw = K @ inv(T_wc)[:3,:] (processor.py:311), row-major 3x4
+ *   box     [SV][4] float   detected box sides in pixels, order x_min,x_max,y_min,y_max
+ *                           (= -line[-1] of the reference's line dicts, sq_libs.py:449)
+ *   mask    [SV][4] uint8   1 = side present (sides within 20 px of the image border are dropped by the
+ *                           caller, quadric_helper.py:87-107), 0 = absent
+ *   prior   [8][9]  float   per-class 3x3 matrices of src/super_quadric/scale_prior, or NULL = no prior
+ *   loss    [n][n_iters] float  total loss (2-D term + prior) BEFORE each step = the reference's loss_log
+ *   status  [n]     int32   bit flags ODAM_SQ_ST_*
+ *
+ * Pointers of the *_host entry points are HOST memory (copies happen inside, on an internal stream,
+ * and the call returns when the results are in the output buffers).  Pointers of the other entry
+ * points are DEVICE memory on the current CUDA device; the work is enqueued on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream) and the call returns without synchronising.
+ *
+ * Error convention: 0 = success, negative = ODAM_SQ_ERR_*; never throws, never aborts.
+ * Thread safety: one host thread per device at a time (the *_host calls share a per-device workspace).
+ */
+#ifndef ODAM_SQ_H_
+#define ODAM_SQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODAM_SQ_ABI_VERSION 1
+#define ODAM_SQ_N_SAMPLES 1000 /* sq_libs.py:545  EqualDistanceSamplerSQ(1000) */
+#define ODAM_SQ_GRID 201       /* _sampler.pyx:423 buffer_size */
+#define ODAM_SQ_N_PARAMS 9
+
+/* representation (sq_libs.py:363-387) */
+#define ODAM_SQ_REPR_SUPER_QUADRIC 0 /* shapes optimised, lr_shape                    */
+#define ODAM_SQ_REPR_CUBE 1          /* shapes frozen (caller passes h = -10000)      */
+#define ODAM_SQ_REPR_QUADRIC 2       /* shapes frozen (caller passes h = -0)          */
+
+/* status bits */
+#define ODAM_SQ_ST_NONFINITE 1   /* a parameter, gradient or loss became NaN/Inf (the reference would raise
+                                    from torch anomaly mode, sq_libs.py:456)                                */
+#define ODAM_SQ_ST_SAMPLER 2     /* degenerate geometry inside the equal-arc-length sampler (NaN split)     */
+#define ODAM_SQ_ST_NO_VALID_PT 4 /* some masked-in side of some view had no point with z > 0.5 (+-1e6 used) */
+
+/* error codes */
+#define ODAM_SQ_OK 0
+#define ODAM_SQ_ERR_ARG (-1)     /* NULL/negative/inconsistent argument          */
+#define ODAM_SQ_ERR_CUDA (-2)    /* a CUDA runtime call failed; see odam_sq_last_cuda_error() */
+#define ODAM_SQ_ERR_DEVICE (-3)  /* device is not compute capability 10.x        */
+#define ODAM_SQ_ERR_CONFIG (-4)  /* launch configuration not realisable          */
+
+/* Optional knobs and test-only inputs/outputs; zero-initialise, then set what you need. */
+typedef struct odam_sq_options {
+    int threads;            /* CTA size (multiple of 32, 32..1024); 0 = choose from the view counts   */
+    int max_slices;         /* max point-slices per view (1..8); 0 = default                           */
+    int max_views;          /* device-pointer entry only: max views of any object, if the caller knows it
+                               (with threads != 0 this avoids reading view_off back to the host)         */
+    /* teacher forcing (tests): start from a recorded optimiser state instead of a fresh one          */
+    const float *m0;        /* [n][9] Adam exp_avg     (NULL = zeros)                                  */
+    const float *v0;        /* [n][9] Adam exp_avg_sq  (NULL = zeros)                                  */
+    int step0;              /* Adam steps already taken                                                */
+    const float *s0;        /* [n][3] prior anchor scales (NULL = the scales in `init`, sq_libs.py:454) */
+    /* extra outputs (any may be NULL)                                                                 */
+    float *out_m;           /* [n][9]                                                                  */
+    float *out_v;           /* [n][9]                                                                  */
+    float *out_grad;        /* [n][9]  gradient of the LAST iteration                                  */
+    float *out_pred;        /* [SV][4] predicted box sides of the LAST iteration                       */
+    int32_t *out_arg;       /* [SV][4] arg-extreme sample index of the LAST iteration (-1 = sentinel)  */
+    uint8_t *out_eta_idx;   /* [n][1000] eta-grid index of every sample, LAST iteration                */
+    float *out_grids;       /* [n][2][201] eta grid then omega grid, LAST iteration                    */
+    float *out_param_hist;  /* [n][n_iters][9] parameters after every step                             */
+} odam_sq_options;
+
+int odam_sq_abi_version(void);
+const char *odam_sq_error_string(int code);
+const char *odam_sq_last_cuda_error(void);
+
+/* Loads the sampler's constant tables (the 2000 uniforms of mt19937(seed=0), sampling.cpp:18-28,169)
+ * onto `device` and sizes the kernels' shared memory.  Idempotent; called lazily by every entry point. */
+int odam_sq_init(int device);
+
+/* SuperQuadricOptimizer.run for n objects at once (sq_libs.py:432-475).  Device pointers. */
+int odam_sq_optimize(const float *init, const int32_t *cls, const int32_t *view_off,
+                     const float *Ms, const float *box, const uint8_t *mask, const float *prior,
+                     int n, int n_iters, int representation, float lr, float lr_shape,
+                     float *out_params, float *out_loss, int32_t *out_status,
+                     const odam_sq_options *opt, void *stream);
+
+/* Same, HOST pointers; total_views = view_off[n].  This is what the Python drop-in calls. */
+int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *view_off,
+                          const float *Ms, const float *box, const uint8_t *mask, const float *prior,
+                          int n, int n_iters, int representation, float lr, float lr_shape,
+                          float *out_params, float *out_loss, int32_t *out_status,
+                          const odam_sq_options *opt, int device);
+
+/* compute_ellipsoid_points (sq_libs.py:577-595): params[n][9] -> xyz[n][1000][3] world points. */
+int odam_sq_sample_points(const float *params, int n, float *out_xyz, void *stream);
+int odam_sq_sample_points_host(const float *params, int n, float *out_xyz, int device);
+
+/* get_bbox (sq_libs.py:547-554) for every (object, view): out_box[SV][4] = x_min,x_max,y_min,y_max of the
+ * projected samples (no validity test, plain division by z, as the reference does there). */
+int odam_sq_project_boxes(const float *params, const int32_t *view_off, const float *Ms, int n,
+                          float *out_box, void *stream);
+int odam_sq_project_boxes_host(const float *params, const int32_t *view_off, const float *Ms, int n,
+                               float *out_box, int device);
+
+/* Drop-in for the reference's own native entry point, fast_sampler/sampling.hpp:5-15
+ *   void sample_on_batch(float *shapes, float *epsilons, float *etas, float *omegas, int B, int M, int N,
+ *                        int buffer_size, int seed)
+ * as bound by _sampler.pyx:413-441 (N = 1000, buffer_size = 201, seed = 0 are the only values that path uses;
+ * anything else is ODAM_SQ_ERR_ARG).  shapes[B][M][3], epsilons[B][M][2] -> etas, omegas [B][M][N]; HOST pointers. */
+int odam_sq_sample_on_batch_host(const float *shapes, const float *epsilons, float *etas, float *omegas,
+                                 int B, int M, int N, int buffer_size, int seed, int device);
+
+/* The launch configuration odam_sq_optimize would use (for benchmarks/logging). */
+int odam_sq_query_launch(const int32_t *view_off_host, int n, const odam_sq_options *opt,
+                         int *threads, int *smem_bytes, int *ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODAM_SQ_H_ */

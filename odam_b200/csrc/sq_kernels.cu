@@ -1,0 +1,944 @@
+// sq_kernels.cu -- fused multi-view superquadric optimiser for B200 (sm_100a) + its C ABI (include/odam_sq.h).
+//
+// One CTA per object, one persistent launch for all iterations.  Per iteration, entirely on chip:
+//   A  derived quantities (a = s^2, e = 0.2 + 1.4 sigmoid(h), rotation)                  [sq_libs.py:577-584]
+//   B  two 201-entry equal-arc-length grids, one warp each, level-synchronous            [sampling.cpp:76-125]
+//   C  sequential fp32 CDF + normalisation (warp 0, overlapping the omega grid of warp 1) [sampling.cpp:137-148]
+//   D  per sample: CDF bisection -> (eta, omega) grid indices -> surface point -> world   [sampling.cpp:151-154,210-212;
+//      point, kept in shared memory (SoA, 12 KB)                                           sampling.py:591-615]
+//   E  per (view, point slice): project all points, track the 4 extrema with 3-input      [sq_libs.py:395-413]
+//      min/max, resolve the arg-extreme index by rescanning one 8-point chunk
+//   F  per (view, side): L1 term and analytic gradient through the arg-extreme point      [sq_libs.py:420-430 + autograd]
+//   G  deterministic CTA reduction of 9 gradients + 4 side sums, prior, Adam              [sq_libs.py:463-472]
+//
+// No tensor cores: the path is FP32 FMA + min/max + one MUFU.RCP per point-view.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "../../include/odam_sq.h"
+#include "sq_device.cuh"
+
+namespace odam {
+
+constexpr int kMaxWarps = 32;
+constexpr int kRed = 13;  // 9 gradients + 4 side sums
+
+struct alignas(16) Smem {
+    float px[kNPad], py[kNPad], pz[kNPad];  // world points, SoA
+    GridTab ge, go;
+    float cdf[kGPad];
+    int queue[2][kGPad];
+    uint8_t pj[kNPad];                      // eta-grid index of each sample
+    float red[kMaxWarps][kRed + 3];
+    float par[12], m[12], v[12], s0[4], grad[12], prior[12];
+    Pose pose;
+    int status;
+    int bad[2];
+};
+
+struct OptArgs {
+    const float *init; const int32_t *cls; const int32_t *view_off;
+    const float *Ms; const float *box; const uint8_t *mask; const float *prior;
+    int n, n_iters, optimize_shapes, max_slices;
+    const float *adam_tab;  // [n_iters][4]: -lr/bc1, -lr_shape/bc1, sqrt(bc2), unused
+    float beta1w, beta2, beta2w, eps;
+    const float *m0, *v0, *s0;
+    float *out_params, *out_loss; int32_t *out_status;
+    float *out_m, *out_v, *out_grad, *out_pred; int32_t *out_arg; uint8_t *out_eta_idx; float *out_grids;
+    float *out_param_hist;
+};
+
+// phases A-D: parameters in S.par -> 1000 world points in S.px/py/pz (+ S.pj, grids)
+__device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nwarps = nthreads >> 5;
+    // ---- A ----
+    if (tid == 0) {
+        Pose &P = S.pose;
+        for (int k = 0; k < 3; k++) { P.a[k] = __fmul_rn(S.par[4 + k], S.par[4 + k]); P.t[k] = S.par[k]; }
+        for (int k = 0; k < 2; k++) {
+            float sg = (float)(1.0 / (1.0 + exp(-(double)S.par[7 + k])));  // torch.sigmoid, correctly rounded
+            P.sig[k] = sg;
+            P.e[k] = __fadd_rn(__fmul_rn(sg, 1.4f), 0.2f);
+        }
+        double sd, cd;
+        sincos((double)S.par[3], &sd, &cd);
+        P.cz = (float)cd; P.sz = (float)sd;
+        S.bad[0] = 0; S.bad[1] = 0;
+    }
+    __syncthreads();
+    // ---- B, C ----
+    const float pi = 3.14159274101257324f;       // (float)acos(-1), sampling.cpp:14
+    const float pi_2 = __fmul_rn(pi, 0.5f);      // pi/2, :15
+    {
+        const Pose &P = S.pose;
+        if (warp == 0) {
+            int bad = 0;
+            build_grid_warp(S.ge, S.queue[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, lane, bad);  // :183-190
+            build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                        // :191-199
+            __syncwarp();
+            patch_zero_angle(S.ge, P.e[0], lane);
+            if (bad) S.bad[0] = 1;
+        }
+        if (warp == (nwarps > 1 ? 1 : 0)) {
+            int bad = 0;
+            build_grid_warp(S.go, S.queue[1], P.a[0], P.a[1], P.e[1], pi, -pi, lane, bad);      // :202-209
+            __syncwarp();
+            patch_zero_angle(S.go, P.e[1], lane);
+            if (bad) S.bad[1] = 1;
+        }
+    }
+    __syncthreads();
+    // ---- D ----
+    {
+        const Pose P = S.pose;
+        for (int i = tid; i < kNPad; i += nthreads) {
+            if (i < kN) {
+                int j = lower_bound_201(S.cdf, g_u_eta[i]);
+                int k = g_k_omega[i];
+                float x0, y0, z0, X, Y, Z;
+                local_point(P, S.ge, S.go, j, k, x0, y0, z0);
+                to_world(P, clamp_eps(x0), clamp_eps(y0), clamp_eps(z0), X, Y, Z);
+                S.px[i] = X; S.py[i] = Y; S.pz[i] = Z; S.pj[i] = (uint8_t)j;
+            } else {  // padding: never valid (NaN is ignored by min/max)
+                float nanv = __int_as_float(0x7fc00000);
+                S.px[i] = nanv; S.py[i] = nanv; S.pz[i] = nanv; S.pj[i] = 0;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void load_M(const float *Ms, int gv, float (&M)[12])
+{
+    const float4 *p = reinterpret_cast<const float4 *>(Ms + (size_t)gv * 12);
+    float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+    M[0] = r0.x; M[1] = r0.y; M[2] = r0.z; M[3] = r0.w;
+    M[4] = r1.x; M[5] = r1.y; M[6] = r1.z; M[7] = r1.w;
+    M[8] = r2.x; M[9] = r2.y; M[10] = r2.z; M[11] = r2.w;
+}
+
+// phase E for one (view, slice) item: extrema over chunks [c0, c1) and the arg index of each
+__device__ __forceinline__ void scan_item(const Smem &S, const float (&M)[12], int c0, int c1,
+                                          float (&best)[4], int (&arg)[4])
+{
+    best[0] = 1000000.f; best[1] = -1000000.f; best[2] = 1000000.f; best[3] = -1000000.f;
+    int cid[4] = {-1, -1, -1, -1};
+    for (int c = c0; c < c1; c++) {
+        const float4 *xs = reinterpret_cast<const float4 *>(S.px + c * kChunk);
+        const float4 *ys = reinterpret_cast<const float4 *>(S.py + c * kChunk);
+        const float4 *zs = reinterpret_cast<const float4 *>(S.pz + c * kChunk);
+        float u[kChunk], w[kChunk];
+#pragma unroll
+        for (int h = 0; h < kChunk / 4; h++) {
+            float4 x = xs[h], y = ys[h], z = zs[h];
+            project_uv(M, x.x, y.x, z.x, u[4 * h + 0], w[4 * h + 0]);
+            project_uv(M, x.y, y.y, z.y, u[4 * h + 1], w[4 * h + 1]);
+            project_uv(M, x.z, y.z, z.z, u[4 * h + 2], w[4 * h + 2]);
+            project_uv(M, x.w, y.w, z.w, u[4 * h + 3], w[4 * h + 3]);
+        }
+        float n0 = best[0], n1 = best[1], n2 = best[2], n3 = best[3];
+#pragma unroll
+        for (int h = 0; h < kChunk; h += 2) {
+            n0 = fmin3(n0, u[h], u[h + 1]);
+            n1 = fmax3(n1, u[h], u[h + 1]);
+            n2 = fmin3(n2, w[h], w[h + 1]);
+            n3 = fmax3(n3, w[h], w[h + 1]);
+        }
+        // strict improvement only: the first chunk (lowest indices) keeps ties
+        if (n0 < best[0]) { best[0] = n0; cid[0] = c; }
+        if (n1 > best[1]) { best[1] = n1; cid[1] = c; }
+        if (n2 < best[2]) { best[2] = n2; cid[2] = c; }
+        if (n3 > best[3]) { best[3] = n3; cid[3] = c; }
+    }
+    // resolve the index: first point of the recorded chunk whose (bit-identical) projection equals the extremum
+#pragma unroll
+    for (int sd = 0; sd < 4; sd++) {
+        arg[sd] = -1;
+        if (cid[sd] >= 0) {
+            int base = cid[sd] * kChunk;
+            int found = -1;
+#pragma unroll
+            for (int h = kChunk - 1; h >= 0; h--) {
+                float u, w;
+                project_uv(M, S.px[base + h], S.py[base + h], S.pz[base + h], u, w);
+                if ((sd < 2 ? u : w) == best[sd]) found = base + h;
+            }
+            arg[sd] = found;
+        }
+    }
+}
+
+template <int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+    const int obj = blockIdx.x;
+    const int v_begin = A.view_off[obj];
+    const int V = A.view_off[obj + 1] - v_begin;
+    // per-item results live after the fixed part of shared memory
+    float *ext_val = reinterpret_cast<float *>(smem_raw + sizeof(Smem));
+
+    int slices = V > 0 ? T / V : 1;
+    slices = max(1, min(slices, A.max_slices));
+    const int n_items = V * slices;
+    int *ext_arg = reinterpret_cast<int *>(ext_val + 4 * n_items);
+
+    if (tid < 9) {
+        S.par[tid] = A.init[(size_t)obj * 9 + tid];
+        S.m[tid] = A.m0 ? A.m0[(size_t)obj * 9 + tid] : 0.f;
+        S.v[tid] = A.v0 ? A.v0[(size_t)obj * 9 + tid] : 0.f;
+        if (A.prior) S.prior[tid] = A.prior[(size_t)A.cls[obj] * 9 + tid];
+    }
+    if (tid < 3) S.s0[tid] = A.s0 ? A.s0[(size_t)obj * 3 + tid] : A.init[(size_t)obj * 9 + 4 + tid];
+    if (tid == 0) S.status = 0;
+    __syncthreads();
+
+    const float invV = V > 0 ? __fdiv_rn(1.f, (float)V) : 0.f;
+
+    for (int it = 0; it < A.n_iters; it++) {
+        sample_surface(S, tid, T);
+        const bool last = it == A.n_iters - 1;
+
+        // ---- E ----
+        for (int item = tid; item < n_items; item += T) {
+            int sl = item / V, v = item - sl * V;
+            float M[12];
+            load_M(A.Ms, v_begin + v, M);
+            int c0 = (sl * kNChunks) / slices, c1 = ((sl + 1) * kNChunks) / slices;
+            float best[4];
+            int arg[4];
+            scan_item(S, M, c0, c1, best, arg);
+#pragma unroll
+            for (int sd = 0; sd < 4; sd++) { ext_val[item * 4 + sd] = best[sd]; ext_arg[item * 4 + sd] = arg[sd]; }
+        }
+        __syncthreads();
+
+        // ---- F ----
+        float acc[kRed];
+#pragma unroll
+        for (int k = 0; k < kRed; k++) acc[k] = 0.f;
+        const Pose P = S.pose;
+        for (int pr = tid; pr < 4 * V; pr += T) {
+            int v = pr >> 2, sd = pr & 3;
+            // combine slices in index order; strict comparison keeps the first index on ties
+            float best = ext_val[v * 4 + sd];
+            int arg = ext_arg[v * 4 + sd];
+            for (int sl = 1; sl < slices; sl++) {
+                float b = ext_val[(sl * V + v) * 4 + sd];
+                bool better = (sd & 1) ? (b > best) : (b < best);
+                if (better) { best = b; arg = ext_arg[(sl * V + v) * 4 + sd]; }
+            }
+            int gv = v_begin + v;
+            float target = A.box[(size_t)gv * 4 + sd];
+            float mk = A.mask[(size_t)gv * 4 + sd] ? 1.f : 0.f;
+            float diff = __fsub_rn(best, target);
+            float l = fabsf(diff);
+            if (!(l == l)) l = 0.f;  // sq_libs.py:426-427
+            acc[9 + sd] = __fadd_rn(acc[9 + sd], __fmul_rn(l, mk));
+            if (last) {
+                if (A.out_pred) A.out_pred[(size_t)gv * 4 + sd] = best;
+                if (A.out_arg) A.out_arg[(size_t)gv * 4 + sd] = arg;
+            }
+            if (arg < 0 && mk != 0.f) atomicOr(&S.status, ODAM_SQ_ST_NO_VALID_PT);
+            if (arg < 0 || mk == 0.f || !(diff == diff)) continue;
+            // gradient through the arg-extreme point
+            float c = __fmul_rn(__fmul_rn(sgnf(diff), mk), invV);
+            float M[12];
+            load_M(A.Ms, gv, M);
+            float X = S.px[arg], Y = S.py[arg], Z = S.pz[arg];
+            float qx = __fmaf_rn(X, M[0], __fmaf_rn(Y, M[1], __fmaf_rn(Z, M[2], M[3])));
+            float qy = __fmaf_rn(X, M[4], __fmaf_rn(Y, M[5], __fmaf_rn(Z, M[6], M[7])));
+            float qz = __fmaf_rn(X, M[8], __fmaf_rn(Y, M[9], __fmaf_rn(Z, M[10], M[11])));
+            float d = __fadd_rn(fabsf(qz), 1e-6f);
+            float num = sd < 2 ? qx : qy;
+            float g_lin = __fdiv_rn(c, d);                                        // d(u)/d(q_x or q_y)
+            float g_z = -__fmul_rn(__fdiv_rn(__fmul_rn(c, num), __fmul_rn(d, d)), sgnf(qz));  // d(u)/d(q_z)
+            int r0 = sd < 2 ? 0 : 4;
+            float gp0 = __fmaf_rn(M[8], g_z, __fmul_rn(M[r0 + 0], g_lin));
+            float gp1 = __fmaf_rn(M[9], g_z, __fmul_rn(M[r0 + 1], g_lin));
+            float gp2 = __fmaf_rn(M[10], g_z, __fmul_rn(M[r0 + 2], g_lin));
+            int j = S.pj[arg], k = g_k_omega[arg];
+            float x0, y0, z0;
+            local_point(P, S.ge, S.go, j, k, x0, y0, z0);
+            float x = clamp_eps(x0), y = clamp_eps(y0);
+            acc[0] += gp0; acc[1] += gp1; acc[2] += gp2;
+            acc[3] += gp0 * (-x * P.sz - y * P.cz) + gp1 * (x * P.cz - y * P.sz);
+            float gl0 = (P.cz * gp0 + P.sz * gp1) * clamp_grad(x0);
+            float gl1 = (-P.sz * gp0 + P.cz * gp1) * clamp_grad(y0);
+            float gl2 = gp2 * clamp_grad(z0);
+            float fce = S.ge.fc[j], fse = S.ge.fs[j], fco = S.go.fc[k], fso = S.go.fs[k];
+            acc[4] += 2.f * S.par[4] * (gl0 * fce * fco);
+            acc[5] += 2.f * S.par[5] * (gl1 * fce * fso);
+            acc[6] += 2.f * S.par[6] * (gl2 * fse);
+            if (A.optimize_shapes) {
+                float eta = S.ge.th[j], om = S.go.th[k];
+                if (eta == 0.f) eta = 1e-6f;
+                if (om == 0.f) om = 1e-6f;
+                float lce = logf(fabsf(cosf(eta))), lse = logf(fabsf(sinf(eta)));
+                float lco = logf(fabsf(cosf(om))), lso = logf(fabsf(sinf(om)));
+                float ge1 = (gl0 * x0 + gl1 * y0) * lce + gl2 * z0 * lse;
+                float ge2 = gl0 * x0 * lco + gl1 * y0 * lso;
+                acc[7] += ge1 * 1.4f * P.sig[0] * (1.f - P.sig[0]);
+                acc[8] += ge2 * 1.4f * P.sig[1] * (1.f - P.sig[1]);
+            }
+        }
+        // ---- G: deterministic reduction (butterfly inside the warp, warp order across) ----
+#pragma unroll
+        for (int k = 0; k < kRed; k++) {
+            float x = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+            acc[k] = x;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kRed; k++) S.red[warp][k] = acc[k];
+        }
+        __syncthreads();
+        if (tid < kRed) {
+            float x = 0.f;
+            for (int wi = 0; wi < nwarps; wi++) x += S.red[wi][tid];
+            S.red[0][tid] = x;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // loss = sum over sides of mean over ALL views (sq_libs.py:428-429) + prior (:463-466)
+            float loss = 0.f;
+            for (int sd = 0; sd < 4; sd++) loss = __fadd_rn(loss, __fdiv_rn(S.red[0][9 + sd], (float)V));
+            float g[9];
+            for (int k = 0; k < 9; k++) g[k] = S.red[0][k];
+            if (A.prior) {
+                float d0 = S.s0[0] - S.par[4], d1 = S.s0[1] - S.par[5], d2 = S.s0[2] - S.par[6];
+                float dd[3] = {d0, d1, d2};
+                float q3 = 0.f;
+                for (int r = 0; r < 3; r++) {
+                    float row = 0.f, sym = 0.f;
+                    for (int cc = 0; cc < 3; cc++) {
+                        row = __fmaf_rn(S.prior[3 * r + cc], dd[cc], row);
+                        sym = __fmaf_rn(S.prior[3 * r + cc] + S.prior[3 * cc + r], dd[cc], sym);
+                    }
+                    q3 = __fmaf_rn(dd[r], row, q3);
+                    g[4 + r] += -20.f * sym;
+                }
+                loss = __fadd_rn(loss, __fmul_rn(q3, 20.f));
+            }
+            if (!A.optimize_shapes) { g[7] = 0.f; g[8] = 0.f; }
+            A.out_loss[(size_t)obj * A.n_iters + it] = loss;
+            bool finite = isfinite(loss);
+            for (int k = 0; k < 9; k++) { S.grad[k] = g[k]; finite = finite && isfinite(g[k]); }
+            if (!finite) S.status |= ODAM_SQ_ST_NONFINITE;
+            if (S.bad[0] | S.bad[1]) S.status |= ODAM_SQ_ST_SAMPLER;
+        }
+        __syncthreads();
+        // Adam (torch/optim/adam.py _single_tensor_adam; roundings as probed against torch's CPU kernels)
+        if (tid < (A.optimize_shapes ? 9 : 7)) {
+            float g = S.grad[tid], m = S.m[tid], v = S.v[tid], p = S.par[tid];
+            float alpha = A.adam_tab[it * 4 + (tid < 7 ? 0 : 1)];
+            float bc2s = A.adam_tab[it * 4 + 2];
+            m = __fmaf_rn(A.beta1w, __fsub_rn(g, m), m);
+            v = __fmul_rn(v, A.beta2);
+            v = __fmaf_rn(__fmul_rn(A.beta2w, g), g, v);
+            float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), A.eps);
+            p = __fadd_rn(p, __fdiv_rn(__fmul_rn(alpha, m), denom));
+            S.m[tid] = m; S.v[tid] = v; S.par[tid] = p;
+            if (A.out_param_hist) A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = p;
+        }
+        if (A.out_param_hist && tid >= 7 && tid < 9 && !A.optimize_shapes)
+            A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = S.par[tid];
+        if (last) {
+            if (A.out_eta_idx) for (int i = tid; i < kN; i += T) A.out_eta_idx[(size_t)obj * kN + i] = S.pj[i];
+            if (A.out_grids) for (int i = tid; i < kG; i += T) {
+                A.out_grids[((size_t)obj * 2 + 0) * kG + i] = S.ge.th[i];
+                A.out_grids[((size_t)obj * 2 + 1) * kG + i] = S.go.th[i];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < 9) {
+        float p = S.par[tid];
+        A.out_params[(size_t)obj * 9 + tid] = p;
+        if (!isfinite(p)) atomicOr(&S.status, ODAM_SQ_ST_NONFINITE);
+        if (A.out_m) A.out_m[(size_t)obj * 9 + tid] = S.m[tid];
+        if (A.out_v) A.out_v[(size_t)obj * 9 + tid] = S.v[tid];
+        if (A.out_grad) A.out_grad[(size_t)obj * 9 + tid] = S.grad[tid];
+    }
+    __syncthreads();
+    if (tid == 0 && A.out_status) A.out_status[obj] = S.status;
+}
+
+// forward only: compute_ellipsoid_points for n objects, one CTA each
+__global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int n, float *out_xyz)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, obj = blockIdx.x;
+    if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
+    __syncthreads();
+    sample_surface(S, tid, blockDim.x);
+    for (int i = tid; i < kN; i += blockDim.x) {
+        float *o = out_xyz + ((size_t)obj * kN + i) * 3;
+        o[0] = S.px[i]; o[1] = S.py[i]; o[2] = S.pz[i];
+    }
+}
+
+// The reference's own native entry point (sampling.hpp:5-15 sample_on_batch, B*M primitives, N=1000,
+// buffer_size=201, seed=0): a[n][3], e[n][2] -> etas[n][1000], omegas[n][1000].  One CTA (2 warps) per primitive.
+__global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const float *e, int n, float *etas, float *omegas)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, obj = blockIdx.x;
+    const float pi = 3.14159274101257324f, pi_2 = __fmul_rn(pi, 0.5f);
+    const float a1 = a[obj * 3 + 0], a2 = a[obj * 3 + 1], a3 = a[obj * 3 + 2];
+    const float e1 = e[obj * 2 + 0], e2 = e[obj * 2 + 1];
+    int bad = 0;
+    if (warp == 0) {
+        build_grid_warp(S.ge, S.queue[0], a1, a3, e1, pi_2, -pi_2, lane, bad);
+        build_cdf_warp(S.ge, S.cdf, __fadd_rn(a1, a2), lane);
+    } else {
+        build_grid_warp(S.go, S.queue[1], a1, a2, e2, pi, -pi, lane, bad);
+    }
+    __syncthreads();
+    for (int i = tid; i < kN; i += blockDim.x) {
+        etas[(size_t)obj * kN + i] = S.ge.th[lower_bound_201(S.cdf, g_u_eta[i])];
+        omegas[(size_t)obj * kN + i] = S.go.th[g_k_omega[i]];
+    }
+}
+
+// get_bbox (sq_libs.py:547-554): plain projective division, no validity test; one CTA per object,
+// one thread per view (looping when V > blockDim).
+__global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, const int32_t *view_off,
+                                                        const float *Ms, int n, float *out_box)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, obj = blockIdx.x;
+    if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
+    __syncthreads();
+    sample_surface(S, tid, blockDim.x);
+    const int v_begin = view_off[obj], V = view_off[obj + 1] - v_begin;
+    for (int v = tid; v < V; v += blockDim.x) {
+        float M[12];
+        load_M(Ms, v_begin + v, M);
+        float b0 = INFINITY, b1 = -INFINITY, b2 = INFINITY, b3 = -INFINITY;
+        for (int i = 0; i < kN; i++) {
+            float X = S.px[i], Y = S.py[i], Z = S.pz[i];
+            float qx = __fmaf_rn(X, M[0], __fmaf_rn(Y, M[1], __fmaf_rn(Z, M[2], M[3])));
+            float qy = __fmaf_rn(X, M[4], __fmaf_rn(Y, M[5], __fmaf_rn(Z, M[6], M[7])));
+            float qz = __fmaf_rn(X, M[8], __fmaf_rn(Y, M[9], __fmaf_rn(Z, M[10], M[11])));
+            float u = __fdiv_rn(qx, qz), w = __fdiv_rn(qy, qz);
+            b0 = fminf(b0, u); b1 = fmaxf(b1, u); b2 = fminf(b2, w); b3 = fmaxf(b3, w);
+        }
+        float *o = out_box + (size_t)(v_begin + v) * 4;
+        o[0] = b0; o[1] = b1; o[2] = b2; o[3] = b3;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_cuda_err[256] = "";
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return ODAM_SQ_ERR_CUDA;
+}
+#define CU(x)                                         \
+    do {                                              \
+        cudaError_t e_ = (x);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
+    } while (0)
+
+// libstdc++'s mt19937 + uniform_real_distribution<float> (sampling.cpp:18-28), seed 0 (_sampler.pyx:438)
+static void host_uniforms(uint32_t seed, int n, float *out)
+{
+    std::vector<uint32_t> mt(624);
+    mt[0] = seed;
+    for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    int idx = 624;
+    for (int k = 0; k < n; k++) {
+        if (idx == 624) {
+            for (int i = 0; i < 624; i++) {
+                uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        float r = (float)y / 4294967296.0f;
+        if (r >= 1.0f) r = nextafterf(1.0f, 0.0f);
+        out[k] = r;
+    }
+}
+
+struct DeviceState {
+    bool ready = false;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    // workspace of the *_host entry points
+    cudaStream_t stream = nullptr;
+    void *dbuf = nullptr; size_t dbytes = 0;
+    void *hbuf = nullptr; size_t hbytes = 0;   // pinned staging
+    float *adam_tab = nullptr; int adam_cap = 0;
+    std::vector<float> adam_host; int adam_iters = -1, adam_step0 = -1; double adam_lr = 0, adam_lrs = 0;
+};
+static DeviceState g_dev[64];
+static std::mutex g_mu;
+
+static int ensure_init(int device)
+{
+    if (device < 0 || device >= 64) return ODAM_SQ_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState &D = g_dev[device];
+    if (D.ready) return ODAM_SQ_OK;
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { cudaSetDevice(cur); return ODAM_SQ_ERR_DEVICE; }
+    D.sm_count = prop.multiProcessorCount;
+    D.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    std::vector<float> u(2 * kN);
+    host_uniforms(0u, 2 * kN, u.data());
+    std::vector<uint8_t> kom(kN);
+    for (int i = 0; i < kN; i++) kom[i] = (uint8_t)(int)(u[kN + i] * (float)kG);  // sampling.cpp:211
+    CU(cudaMemcpyToSymbol(g_u_eta, u.data(), sizeof(float) * kN));
+    CU(cudaMemcpyToSymbol(g_k_omega, kom.data(), kN));
+    CU(cudaFuncSetAttribute(sq_optimize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
+    CU(cudaFuncSetAttribute(sq_optimize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
+    CU(cudaFuncSetAttribute(sq_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    CU(cudaFuncSetAttribute(sq_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    CU(cudaFuncSetAttribute(sq_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    CU(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+    CU(cudaSetDevice(cur));
+    D.ready = true;
+    return ODAM_SQ_OK;
+}
+
+struct LaunchCfg { int threads, max_slices, smem; };
+
+// view statistics -> CTA size.  Small tracks get several point slices per view so that a CTA has >=4 warps.
+static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
+                         int smem_optin, LaunchCfg &L)
+{
+    int max_slices = opt && opt->max_slices ? opt->max_slices : 8;
+    if (max_slices < 1 || max_slices > 8) return ODAM_SQ_ERR_ARG;
+    int threads = opt ? opt->threads : 0;
+    if (threads == 0) {
+        // throughput regime (many objects per SM): ~160 threads; latency regime (fewer CTAs than SMs): wider
+        int target = n >= 2 * sm_count ? 160 : 512;
+        int v = std::max(1, (int)(mean_views + 0.5));
+        int s = std::max(1, std::min(max_slices, target / v));
+        threads = ((v * s + 31) / 32) * 32;
+        threads = std::max(64, std::min(1024, threads));
+    }
+    if (threads % 32 || threads < 32 || threads > 1024) return ODAM_SQ_ERR_ARG;
+    long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
+    long smem = (long)sizeof(Smem) + items * 4 * 8;
+    if (smem > smem_optin) return ODAM_SQ_ERR_CONFIG;
+    L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem;
+    return ODAM_SQ_OK;
+}
+
+static void fill_adam_tab(std::vector<float> &tab, int n_iters, int step0, double lr, double lr_shape)
+{
+    tab.resize((size_t)n_iters * 4);
+    for (int it = 0; it < n_iters; it++) {
+        double step = (double)(step0 + it + 1);
+        double bc1 = 1.0 - pow(0.9, step), bc2 = 1.0 - pow(0.999, step);
+        tab[it * 4 + 0] = (float)(-(lr / bc1));
+        tab[it * 4 + 1] = (float)(-(lr_shape / bc1));
+        tab[it * 4 + 2] = (float)pow(bc2, 0.5);
+        tab[it * 4 + 3] = 0.f;
+    }
+}
+
+static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L, cudaStream_t st)
+{
+    OptArgs A = A0;
+    A.max_slices = L.max_slices;
+    A.beta1w = (float)(1.0 - 0.9); A.beta2 = (float)0.999; A.beta2w = (float)(1.0 - 0.999); A.eps = (float)1e-8;
+    if (L.threads <= 256) sq_optimize_kernel<256><<<A.n, L.threads, L.smem, st>>>(A);
+    else sq_optimize_kernel<1024><<<A.n, L.threads, L.smem, st>>>(A);
+    CU(cudaGetLastError());
+    return ODAM_SQ_OK;
+}
+
+struct Carver {  // hands out 256-byte aligned offsets into one packed staging buffer
+    size_t off = 0;
+    template <class T> size_t take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        size_t at = off;
+        off += sizeof(T) * count;
+        return at;
+    }
+};
+int ensure_ws(DeviceState &D, size_t bytes)
+{
+    if (D.dbytes < bytes) {
+        if (D.dbuf) cudaFree(D.dbuf);
+        if (D.hbuf) cudaFreeHost(D.hbuf);
+        D.dbuf = D.hbuf = nullptr; D.dbytes = D.hbytes = 0;
+        size_t cap = bytes + bytes / 4 + (1 << 20);
+        CU(cudaMalloc(&D.dbuf, cap));
+        CU(cudaMallocHost(&D.hbuf, cap));
+        D.dbytes = D.hbytes = cap;
+    }
+    return ODAM_SQ_OK;
+}
+
+}  // namespace odam
+
+using namespace odam;
+
+extern "C" {
+
+int odam_sq_abi_version(void) { return ODAM_SQ_ABI_VERSION; }
+
+const char *odam_sq_error_string(int code)
+{
+    switch (code) {
+        case ODAM_SQ_OK: return "ok";
+        case ODAM_SQ_ERR_ARG: return "invalid argument";
+        case ODAM_SQ_ERR_CUDA: return "CUDA runtime error";
+        case ODAM_SQ_ERR_DEVICE: return "device is not compute capability 10.x (B200 required)";
+        case ODAM_SQ_ERR_CONFIG: return "launch configuration not realisable (too many views for shared memory)";
+        default: return "unknown error";
+    }
+}
+
+const char *odam_sq_last_cuda_error(void) { return g_cuda_err; }
+
+int odam_sq_init(int device) { return ensure_init(device); }
+
+int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *opt, int *threads, int *smem_bytes,
+                         int *ctas_per_sm)
+{
+    if (!view_off || n <= 0) return ODAM_SQ_ERR_ARG;
+    int maxv = 0;
+    for (int i = 0; i < n; i++) maxv = std::max(maxv, view_off[i + 1] - view_off[i]);
+    LaunchCfg L;
+    int rc = choose_launch(maxv, (double)(view_off[n] - view_off[0]) / n, n, opt, 148, 232448, L);
+    if (rc) return rc;
+    if (threads) *threads = L.threads;
+    if (smem_bytes) *smem_bytes = L.smem;
+    if (ctas_per_sm) *ctas_per_sm = std::min({32, 2048 / L.threads, (233472 - 1024) / (L.smem + 1024)});
+    return ODAM_SQ_OK;
+}
+
+// device-pointer entry: view statistics are needed on the host to pick the CTA size, so the caller's
+// options may carry them (threads != 0); otherwise view_off is read back (one small D2H copy).
+int odam_sq_optimize(const float *init, const int32_t *cls, const int32_t *view_off, const float *Ms,
+                     const float *box, const uint8_t *mask, const float *prior, int n, int n_iters,
+                     int representation, float lr, float lr_shape, float *out_params, float *out_loss,
+                     int32_t *out_status, const odam_sq_options *opt, void *stream)
+{
+    if (!init || !view_off || !Ms || !box || !mask || !out_params || !out_loss || n < 0 || n_iters < 0)
+        return ODAM_SQ_ERR_ARG;
+    if (prior && !cls) return ODAM_SQ_ERR_ARG;
+    if (representation < 0 || representation > 2) return ODAM_SQ_ERR_ARG;
+    if (n == 0 || n_iters == 0) return ODAM_SQ_OK;
+    int device = 0;
+    CU(cudaGetDevice(&device));
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    cudaStream_t st = (cudaStream_t)stream;
+    int maxv = opt ? opt->max_views : 0;
+    double meanv = maxv;
+    if (!(opt && opt->threads && maxv > 0)) {
+        std::vector<int32_t> voff(n + 1);
+        CU(cudaMemcpyAsync(voff.data(), view_off, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        maxv = 0;
+        for (int i = 0; i < n; i++) {
+            if (voff[i + 1] < voff[i]) return ODAM_SQ_ERR_ARG;
+            maxv = std::max(maxv, voff[i + 1] - voff[i]);
+        }
+        meanv = (double)(voff[n] - voff[0]) / n;
+    }
+    LaunchCfg L;
+    rc = choose_launch(maxv, meanv, n, opt, D.sm_count, D.max_smem_optin, L);
+    if (rc) return rc;
+    // Adam bias-correction table (host doubles, as torch computes them in Python floats); cached per device
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int step0 = opt ? opt->step0 : 0;
+        if (D.adam_iters != n_iters || D.adam_step0 != step0 || D.adam_lr != (double)lr || D.adam_lrs != (double)lr_shape) {
+            CU(cudaStreamSynchronize(st));  // a previous launch may still read the old table
+            if (D.adam_cap < n_iters) {
+                if (D.adam_tab) cudaFree(D.adam_tab);
+                D.adam_tab = nullptr;
+                CU(cudaMalloc(&D.adam_tab, sizeof(float) * 4 * n_iters));
+                D.adam_cap = n_iters;
+            }
+            fill_adam_tab(D.adam_host, n_iters, step0, (double)lr, (double)lr_shape);
+            CU(cudaMemcpyAsync(D.adam_tab, D.adam_host.data(), sizeof(float) * D.adam_host.size(),
+                               cudaMemcpyHostToDevice, st));
+            D.adam_iters = n_iters; D.adam_step0 = step0; D.adam_lr = (double)lr; D.adam_lrs = (double)lr_shape;
+        }
+    }
+    OptArgs A;
+    memset(&A, 0, sizeof A);
+    A.init = init; A.cls = cls; A.view_off = view_off; A.Ms = Ms; A.box = box; A.mask = mask; A.prior = prior;
+    A.n = n; A.n_iters = n_iters; A.optimize_shapes = representation == ODAM_SQ_REPR_SUPER_QUADRIC;
+    A.adam_tab = D.adam_tab;
+    A.out_params = out_params; A.out_loss = out_loss; A.out_status = out_status;
+    if (opt) {
+        A.m0 = opt->m0; A.v0 = opt->v0; A.s0 = opt->s0;
+        A.out_m = opt->out_m; A.out_v = opt->out_v; A.out_grad = opt->out_grad; A.out_pred = opt->out_pred;
+        A.out_arg = opt->out_arg; A.out_eta_idx = opt->out_eta_idx; A.out_grids = opt->out_grids;
+        A.out_param_hist = opt->out_param_hist;
+    }
+    return launch_optimize(D, A, L, st);
+}
+
+int odam_sq_sample_points(const float *params, int n, float *out_xyz, void *stream)
+{
+    if (!params || !out_xyz || n < 0) return ODAM_SQ_ERR_ARG;
+    if (n == 0) return ODAM_SQ_OK;
+    int device = 0;
+    CU(cudaGetDevice(&device));
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    sq_points_kernel<<<n, 256, sizeof(Smem), (cudaStream_t)stream>>>(params, n, out_xyz);
+    CU(cudaGetLastError());
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_project_boxes(const float *params, const int32_t *view_off, const float *Ms, int n, float *out_box,
+                          void *stream)
+{
+    if (!params || !view_off || !Ms || !out_box || n < 0) return ODAM_SQ_ERR_ARG;
+    if (n == 0) return ODAM_SQ_OK;
+    int device = 0;
+    CU(cudaGetDevice(&device));
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    sq_boxes_kernel<<<n, 256, sizeof(Smem), (cudaStream_t)stream>>>(params, view_off, Ms, n, out_box);
+    CU(cudaGetLastError());
+    return ODAM_SQ_OK;
+}
+
+// ---- host-pointer entry points: H2D, kernel, D2H on the library's own stream ----
+
+int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *view_off, const float *Ms,
+                          const float *box, const uint8_t *mask, const float *prior, int n, int n_iters,
+                          int representation, float lr, float lr_shape, float *out_params, float *out_loss,
+                          int32_t *out_status, const odam_sq_options *opt, int device)
+{
+    if (!init || !view_off || !Ms || !box || !mask || !out_params || !out_loss || n < 0 || n_iters < 0)
+        return ODAM_SQ_ERR_ARG;
+    if (prior && !cls) return ODAM_SQ_ERR_ARG;
+    if (representation < 0 || representation > 2) return ODAM_SQ_ERR_ARG;
+    if (n == 0 || n_iters == 0) return ODAM_SQ_OK;
+    int maxv = 0;
+    for (int i = 0; i < n; i++) {
+        if (view_off[i + 1] < view_off[i]) return ODAM_SQ_ERR_ARG;
+        maxv = std::max(maxv, view_off[i + 1] - view_off[i]);
+    }
+    if (view_off[0] != 0) return ODAM_SQ_ERR_ARG;
+    const size_t SV = (size_t)view_off[n];
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    CU(cudaSetDevice(device));
+    LaunchCfg L;
+    rc = choose_launch(maxv, (double)SV / n, n, opt, D.sm_count, D.max_smem_optin, L);
+    if (rc) { cudaSetDevice(cur); return rc; }
+
+    // one packed staging buffer: inputs first, outputs after; same layout on host (pinned) and device
+    size_t in_bytes = 0, total = 0;
+    size_t o_init, o_cls, o_voff, o_Ms, o_box, o_mask, o_prior, o_tab, o_m0, o_v0, o_s0;
+    size_t o_par, o_loss, o_st, o_m, o_v, o_g, o_pred, o_arg, o_eta, o_grids, o_hist;
+    auto lay = [&](Carver &C) {
+        o_init = C.take<float>((size_t)n * 9); o_cls = C.take<int32_t>(n);
+        o_voff = C.take<int32_t>(n + 1); o_Ms = C.take<float>(SV * 12);
+        o_box = C.take<float>(SV * 4); o_mask = C.take<uint8_t>(SV * 4);
+        o_prior = C.take<float>(72); o_tab = C.take<float>((size_t)n_iters * 4);
+        o_m0 = C.take<float>((size_t)n * 9); o_v0 = C.take<float>((size_t)n * 9);
+        o_s0 = C.take<float>((size_t)n * 3);
+        in_bytes = (C.off + 255) & ~(size_t)255;
+        o_par = C.take<float>((size_t)n * 9); o_loss = C.take<float>((size_t)n * n_iters);
+        o_st = C.take<int32_t>(n);
+        o_m = C.take<float>((size_t)n * 9); o_v = C.take<float>((size_t)n * 9);
+        o_g = C.take<float>((size_t)n * 9); o_pred = C.take<float>(SV * 4);
+        o_arg = C.take<int32_t>(SV * 4);
+        o_eta = C.take<uint8_t>(opt && opt->out_eta_idx ? (size_t)n * kN : 0);
+        o_grids = C.take<float>(opt && opt->out_grids ? (size_t)n * 2 * kG : 0);
+        o_hist = C.take<float>(opt && opt->out_param_hist ? (size_t)n * n_iters * 9 : 0);
+        total = C.off;
+    };
+    { Carver C; lay(C); }
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        rc = ensure_ws(D, total);
+    }
+    if (rc) { cudaSetDevice(cur); return rc; }
+    unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
+    memcpy(h + o_init, init, sizeof(float) * 9 * n);
+    if (cls) memcpy(h + o_cls, cls, sizeof(int32_t) * n);
+    memcpy(h + o_voff, view_off, sizeof(int32_t) * (n + 1));
+    memcpy(h + o_Ms, Ms, sizeof(float) * 12 * SV);
+    memcpy(h + o_box, box, sizeof(float) * 4 * SV);
+    memcpy(h + o_mask, mask, SV * 4);
+    if (prior) memcpy(h + o_prior, prior, sizeof(float) * 72);
+    std::vector<float> tab;
+    fill_adam_tab(tab, n_iters, opt ? opt->step0 : 0, (double)lr, (double)lr_shape);
+    memcpy(h + o_tab, tab.data(), sizeof(float) * tab.size());
+    if (opt && opt->m0) memcpy(h + o_m0, opt->m0, sizeof(float) * 9 * n);
+    if (opt && opt->v0) memcpy(h + o_v0, opt->v0, sizeof(float) * 9 * n);
+    if (opt && opt->s0) memcpy(h + o_s0, opt->s0, sizeof(float) * 3 * n);
+    cudaStream_t st = D.stream;
+    CU(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
+
+    OptArgs A;
+    memset(&A, 0, sizeof A);
+    A.init = (float *)(d + o_init); A.cls = cls ? (int32_t *)(d + o_cls) : nullptr;
+    A.view_off = (int32_t *)(d + o_voff); A.Ms = (float *)(d + o_Ms); A.box = (float *)(d + o_box);
+    A.mask = d + o_mask; A.prior = prior ? (float *)(d + o_prior) : nullptr;
+    A.n = n; A.n_iters = n_iters; A.optimize_shapes = representation == ODAM_SQ_REPR_SUPER_QUADRIC;
+    A.adam_tab = (float *)(d + o_tab);
+    A.out_params = (float *)(d + o_par); A.out_loss = (float *)(d + o_loss); A.out_status = (int32_t *)(d + o_st);
+    if (opt) {
+        A.m0 = opt->m0 ? (float *)(d + o_m0) : nullptr; A.v0 = opt->v0 ? (float *)(d + o_v0) : nullptr;
+        A.s0 = opt->s0 ? (float *)(d + o_s0) : nullptr;
+        A.out_m = opt->out_m ? (float *)(d + o_m) : nullptr; A.out_v = opt->out_v ? (float *)(d + o_v) : nullptr;
+        A.out_grad = opt->out_grad ? (float *)(d + o_g) : nullptr;
+        A.out_pred = opt->out_pred ? (float *)(d + o_pred) : nullptr;
+        A.out_arg = opt->out_arg ? (int32_t *)(d + o_arg) : nullptr;
+        A.out_eta_idx = opt->out_eta_idx ? d + o_eta : nullptr;
+        A.out_grids = opt->out_grids ? (float *)(d + o_grids) : nullptr;
+        A.out_param_hist = opt->out_param_hist ? (float *)(d + o_hist) : nullptr;
+    }
+    rc = launch_optimize(D, A, L, st);
+    if (rc) { cudaSetDevice(cur); return rc; }
+    CU(cudaMemcpyAsync(h + in_bytes, d + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(out_params, h + o_par, sizeof(float) * 9 * n);
+    memcpy(out_loss, h + o_loss, sizeof(float) * (size_t)n * n_iters);
+    if (out_status) memcpy(out_status, h + o_st, sizeof(int32_t) * n);
+    if (opt) {
+        if (opt->out_m) memcpy(opt->out_m, h + o_m, sizeof(float) * 9 * n);
+        if (opt->out_v) memcpy(opt->out_v, h + o_v, sizeof(float) * 9 * n);
+        if (opt->out_grad) memcpy(opt->out_grad, h + o_g, sizeof(float) * 9 * n);
+        if (opt->out_pred) memcpy(opt->out_pred, h + o_pred, sizeof(float) * 4 * SV);
+        if (opt->out_arg) memcpy(opt->out_arg, h + o_arg, sizeof(int32_t) * 4 * SV);
+        if (opt->out_eta_idx) memcpy(opt->out_eta_idx, h + o_eta, (size_t)n * kN);
+        if (opt->out_grids) memcpy(opt->out_grids, h + o_grids, sizeof(float) * 2 * kG * n);
+        if (opt->out_param_hist) memcpy(opt->out_param_hist, h + o_hist, sizeof(float) * 9 * (size_t)n * n_iters);
+    }
+    CU(cudaSetDevice(cur));
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_sample_points_host(const float *params, int n, float *out_xyz, int device)
+{
+    if (!params || !out_xyz || n < 0) return ODAM_SQ_ERR_ARG;
+    if (n == 0) return ODAM_SQ_OK;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    CU(cudaSetDevice(device));
+    size_t in_b = ((sizeof(float) * 9 * n + 255) / 256) * 256, out_b = sizeof(float) * 3 * kN * (size_t)n;
+    { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, in_b + out_b); }
+    if (rc) { cudaSetDevice(cur); return rc; }
+    unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
+    memcpy(h, params, sizeof(float) * 9 * n);
+    CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
+    sq_points_kernel<<<n, 256, sizeof(Smem), D.stream>>>((float *)d, n, (float *)(d + in_b));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h + in_b, d + in_b, out_b, cudaMemcpyDeviceToHost, D.stream));
+    CU(cudaStreamSynchronize(D.stream));
+    memcpy(out_xyz, h + in_b, out_b);
+    CU(cudaSetDevice(cur));
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_project_boxes_host(const float *params, const int32_t *view_off, const float *Ms, int n, float *out_box,
+                               int device)
+{
+    if (!params || !view_off || !Ms || !out_box || n < 0) return ODAM_SQ_ERR_ARG;
+    if (n == 0) return ODAM_SQ_OK;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    CU(cudaSetDevice(device));
+    const size_t SV = (size_t)view_off[n];
+    Carver C;
+    size_t o_p = C.take<float>((size_t)n * 9), o_v = C.take<int32_t>(n + 1), o_M = C.take<float>(SV * 12);
+    size_t in_b = (C.off + 255) & ~(size_t)255;
+    size_t out_b = sizeof(float) * 4 * SV;
+    { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, in_b + out_b); }
+    if (rc) { cudaSetDevice(cur); return rc; }
+    unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
+    memcpy(h + o_p, params, sizeof(float) * 9 * n);
+    memcpy(h + o_v, view_off, sizeof(int32_t) * (n + 1));
+    memcpy(h + o_M, Ms, sizeof(float) * 12 * SV);
+    CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
+    sq_boxes_kernel<<<n, 256, sizeof(Smem), D.stream>>>((float *)(d + o_p), (int32_t *)(d + o_v), (float *)(d + o_M), n,
+                                                         (float *)(d + in_b));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h + in_b, d + in_b, out_b, cudaMemcpyDeviceToHost, D.stream));
+    CU(cudaStreamSynchronize(D.stream));
+    memcpy(out_box, h + in_b, out_b);
+    CU(cudaSetDevice(cur));
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_sample_on_batch_host(const float *shapes, const float *epsilons, float *etas, float *omegas, int B, int M,
+                                 int N, int buffer_size, int seed, int device)
+{
+    if (!shapes || !epsilons || !etas || !omegas || B < 0 || M < 0) return ODAM_SQ_ERR_ARG;
+    if (N != kN || buffer_size != kG || seed != 0) return ODAM_SQ_ERR_ARG;  // the only configuration the path uses
+    const int n = B * M;
+    if (n == 0) return ODAM_SQ_OK;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    CU(cudaSetDevice(device));
+    Carver C;
+    size_t o_a = C.take<float>((size_t)n * 3), o_e = C.take<float>((size_t)n * 2);
+    size_t in_b = (C.off + 255) & ~(size_t)255;
+    C.off = in_b;
+    size_t o_eta = C.take<float>((size_t)n * kN), o_om = C.take<float>((size_t)n * kN);
+    { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, C.off); }
+    if (rc) { cudaSetDevice(cur); return rc; }
+    unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
+    memcpy(h + o_a, shapes, sizeof(float) * 3 * n);
+    memcpy(h + o_e, epsilons, sizeof(float) * 2 * n);
+    CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
+    sq_angles_kernel<<<n, 64, sizeof(Smem), D.stream>>>((float *)(d + o_a), (float *)(d + o_e), n, (float *)(d + o_eta),
+                                                         (float *)(d + o_om));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h + in_b, d + in_b, C.off - in_b, cudaMemcpyDeviceToHost, D.stream));
+    CU(cudaStreamSynchronize(D.stream));
+    memcpy(etas, h + o_eta, sizeof(float) * kN * (size_t)n);
+    memcpy(omegas, h + o_om, sizeof(float) * kN * (size_t)n);
+    CU(cudaSetDevice(cur));
+    return ODAM_SQ_OK;
+}
+
+}  // extern "C"
