@@ -131,6 +131,10 @@ int odam_sq_project_boxes_host(const float *params, const int32_t *view_off, con
 int odam_sq_sample_on_batch_host(const float *shapes, const float *epsilons, float *etas, float *omegas,
                                  int B, int M, int N, int buffer_size, int seed, int device);
 
+/* Roofline probe: measured FP32 FMA throughput of `device` (dense independent FFMA chains, no memory traffic),
+ * in TFLOP/s counting an FMA as 2 flop.  Best of 4 timed launches after one warm-up. */
+int odam_sq_fma_peak(int device, double *tflops);
+
 /* The launch configuration odam_sq_optimize would use (for benchmarks/logging). */
 int odam_sq_query_launch(const int32_t *view_off_host, int n, const odam_sq_options *opt,
                          int *threads, int *smem_bytes, int *ctas_per_sm);

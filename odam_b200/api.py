@@ -237,3 +237,17 @@ def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr
                                 p(out["params"]), p(out["loss"]), p(out["status"]), C.byref(o), stream)
     _lib.check(rc)
     return out
+
+
+def fma_peak_tflops(device=0):
+    """Measured FP32 FMA roofline of the device (library micro-benchmark), TFLOP/s."""
+    L = _lib.load()
+    v = C.c_double()
+    _lib.check(L.odam_sq_fma_peak(device, C.byref(v)))
+    return v.value
+
+
+def algorithmic_flops(view_counts, n_iters):
+    """flops(run) = sum_obj iters * (37,000 * V_obj + 30,000) FP32 flop."""
+    v = np.asarray(view_counts, np.float64)
+    return float((n_iters * (37000.0 * v + 30000.0)).sum())

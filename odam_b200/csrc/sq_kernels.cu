@@ -243,6 +243,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
             int gv = v_begin + v;
             float target = A.box[(size_t)gv * 4 + sd];
             float mk = A.mask[(size_t)gv * 4 + sd] ? 1.f : 0.f;
+            // The scan ranks points with a 1-ulp reciprocal; the winner's coordinate is now re-evaluated with the
+            // reference's own rounding sequence (k-ordered FMA chain of the CPU GEMM, IEEE division) so that the
+            // loss carries the same fp32 noise as the reference's instead of an independent sample of it.
+            float M[12];
+            float qx = 0.f, qy = 0.f, qz = 1.f, d = 1.f;
+            if (arg >= 0) {
+                load_M(A.Ms, gv, M);
+                float X = S.px[arg], Y = S.py[arg], Z = S.pz[arg];
+                qx = __fadd_rn(__fmaf_rn(Z, M[2], __fmaf_rn(Y, M[1], __fmul_rn(X, M[0]))), M[3]);
+                qy = __fadd_rn(__fmaf_rn(Z, M[6], __fmaf_rn(Y, M[5], __fmul_rn(X, M[4]))), M[7]);
+                qz = __fadd_rn(__fmaf_rn(Z, M[10], __fmaf_rn(Y, M[9], __fmul_rn(X, M[8]))), M[11]);
+                d = __fadd_rn(fabsf(qz), 1e-6f);
+                best = __fdiv_rn(sd < 2 ? qx : qy, d);
+            }
             float diff = __fsub_rn(best, target);
             float l = fabsf(diff);
             if (!(l == l)) l = 0.f;  // sq_libs.py:426-427
@@ -255,13 +269,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
             if (arg < 0 || mk == 0.f || !(diff == diff)) continue;
             // gradient through the arg-extreme point
             float c = __fmul_rn(__fmul_rn(sgnf(diff), mk), invV);
-            float M[12];
-            load_M(A.Ms, gv, M);
-            float X = S.px[arg], Y = S.py[arg], Z = S.pz[arg];
-            float qx = __fmaf_rn(X, M[0], __fmaf_rn(Y, M[1], __fmaf_rn(Z, M[2], M[3])));
-            float qy = __fmaf_rn(X, M[4], __fmaf_rn(Y, M[5], __fmaf_rn(Z, M[6], M[7])));
-            float qz = __fmaf_rn(X, M[8], __fmaf_rn(Y, M[9], __fmaf_rn(Z, M[10], M[11])));
-            float d = __fadd_rn(fabsf(qz), 1e-6f);
             float num = sd < 2 ? qx : qy;
             float g_lin = __fdiv_rn(c, d);                                        // d(u)/d(q_x or q_y)
             float g_z = -__fmul_rn(__fdiv_rn(__fmul_rn(c, num), __fmul_rn(d, d)), sgnf(qz));  // d(u)/d(q_z)
@@ -444,6 +451,22 @@ __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, cons
         float *o = out_box + (size_t)(v_begin + v) * 4;
         o[0] = b0; o[1] = b1; o[2] = b2; o[3] = b3;
     }
+}
+
+// FP32 FMA-pipe roofline probe: 8 independent FFMA chains per thread, no memory traffic.
+__global__ void __launch_bounds__(1024) fma_peak_kernel(float *sink, int iters, float a, float b)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+            x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+        }
+    }
+    float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456f) sink[0] = r;  // never true; keeps the chains alive
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -772,14 +795,14 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
         o_voff = C.take<int32_t>(n + 1); o_Ms = C.take<float>(SV * 12);
         o_box = C.take<float>(SV * 4); o_mask = C.take<uint8_t>(SV * 4);
         o_prior = C.take<float>(72); o_tab = C.take<float>((size_t)n_iters * 4);
-        o_m0 = C.take<float>((size_t)n * 9); o_v0 = C.take<float>((size_t)n * 9);
-        o_s0 = C.take<float>((size_t)n * 3);
+        o_m0 = C.take<float>(opt && opt->m0 ? (size_t)n * 9 : 0); o_v0 = C.take<float>(opt && opt->v0 ? (size_t)n * 9 : 0);
+        o_s0 = C.take<float>(opt && opt->s0 ? (size_t)n * 3 : 0);
         in_bytes = (C.off + 255) & ~(size_t)255;
         o_par = C.take<float>((size_t)n * 9); o_loss = C.take<float>((size_t)n * n_iters);
         o_st = C.take<int32_t>(n);
-        o_m = C.take<float>((size_t)n * 9); o_v = C.take<float>((size_t)n * 9);
-        o_g = C.take<float>((size_t)n * 9); o_pred = C.take<float>(SV * 4);
-        o_arg = C.take<int32_t>(SV * 4);
+        o_m = C.take<float>(opt && opt->out_m ? (size_t)n * 9 : 0); o_v = C.take<float>(opt && opt->out_v ? (size_t)n * 9 : 0);
+        o_g = C.take<float>(opt && opt->out_grad ? (size_t)n * 9 : 0); o_pred = C.take<float>(opt && opt->out_pred ? SV * 4 : 0);
+        o_arg = C.take<int32_t>(opt && opt->out_arg ? SV * 4 : 0);
         o_eta = C.take<uint8_t>(opt && opt->out_eta_idx ? (size_t)n * kN : 0);
         o_grids = C.take<float>(opt && opt->out_grids ? (size_t)n * 2 * kG : 0);
         o_hist = C.take<float>(opt && opt->out_param_hist ? (size_t)n * n_iters * 9 : 0);
@@ -937,6 +960,39 @@ int odam_sq_sample_on_batch_host(const float *shapes, const float *epsilons, flo
     CU(cudaStreamSynchronize(D.stream));
     memcpy(etas, h + o_eta, sizeof(float) * kN * (size_t)n);
     memcpy(omegas, h + o_om, sizeof(float) * kN * (size_t)n);
+    CU(cudaSetDevice(cur));
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_fma_peak(int device, double *tflops)
+{
+    if (!tflops) return ODAM_SQ_ERR_ARG;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    CU(cudaSetDevice(device));
+    { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, 4096); }
+    if (rc) { cudaSetDevice(cur); return rc; }
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = D.sm_count * 2, threads = 1024;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(e0, D.stream));
+        fma_peak_kernel<<<blocks, threads, 0, D.stream>>>((float *)D.dbuf, iters, 0.999f, 0.001f);
+        CU(cudaEventRecord(e1, D.stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        if (rep) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
     CU(cudaSetDevice(cur));
     return ODAM_SQ_OK;
 }

@@ -1,0 +1,50 @@
+"""Shard independent object tracks across the GPUs of one box.
+
+Objects (and scenes) are independent (reference src/scripts/run_multi_view.py:44-69 has no cross-object
+state), so the data path has NO collective: every rank optimises a contiguous block of objects, balanced by
+the amount of work (sum of views, since cost ~ V per object).  The only communication is one all-gather of
+the final [n, 9] parameters (+ final loss) at the end -- NCCL over NVLink on GPUs, gloo in the CPU tests.
+"""
+import numpy as np
+
+
+def partition_by_views(view_off, world_size):
+    """Contiguous object ranges [lo, hi) per rank, balanced by sum of views.  Returns list of (lo, hi)."""
+    view_off = np.asarray(view_off, np.int64)
+    n = len(view_off) - 1
+    total = int(view_off[-1] - view_off[0])
+    bounds = [0]
+    for r in range(1, world_size):
+        # first object whose prefix work reaches r/world of the total (keeps blocks contiguous and ordered)
+        target = view_off[0] + total * r / world_size
+        k = int(np.searchsorted(view_off, target, side="left"))
+        bounds.append(min(max(k, bounds[-1]), n))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+
+
+def all_gather_rows(local, counts, dist, device=None):
+    """Gather per-rank row blocks [counts[r], C] into the full [sum(counts), C] array on every rank.
+
+    Uses one all_gather_into_tensor over blocks padded to the largest shard (a few KB..MB: latency-bound,
+    NVSwitch makes it uniform), issued on the current stream of `local`'s device.
+    """
+    import torch
+    world = dist.get_world_size()
+    pad = int(max(counts))
+    C = local.shape[1]
+    buf = torch.zeros((pad, C), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    out = torch.empty((world * pad, C), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf)
+    out = out.view(world, pad, C)
+    return torch.cat([out[r, : counts[r]] for r in range(world)], 0)
+
+
+def optimize_sharded(tracks, optimize_fn, dist, rank, world_size):
+    """tracks: the FULL PackedTracks on every rank.  optimize_fn(shard) -> torch [n_shard, C] rows (params,
+    optionally with extra columns) on the rank's device.  Returns the gathered [n, C] tensor."""
+    parts = partition_by_views(tracks.view_off, world_size)
+    lo, hi = parts[rank]
+    local = optimize_fn(tracks.slice(lo, hi))
+    return all_gather_rows(local, [h - l for l, h in parts], dist)

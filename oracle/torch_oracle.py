@@ -65,6 +65,7 @@ def surface_points(translate, angle, scales, shapes, sampler):
     pts = torch.stack([x, y, z], -1)[0, 0]
     pts = pts @ R.T
     pts = pts + translate.unsqueeze(0)
+    surface_points.last_ae = (a.detach().numpy().reshape(3).copy(), e.detach().numpy().reshape(2).copy())
     return pts, etas, omegas
 
 
@@ -135,6 +136,7 @@ def run(translate, angle, dims, Ms, box, mask, prior33=None, n_iters=200,
         out["pred"] = np.zeros((n_iters, V, 4), np.float32)
         out["etas"] = np.zeros((n_iters, 1000), np.float32)
         out["omegas"] = np.zeros((n_iters, 1000), np.float32)
+        out["ae"] = np.zeros((n_iters, 5), np.float32)   # the (a, e) handed to the sampler
     guard = torch.autograd.set_detect_anomaly if anomaly else _NoAnomaly
     try:
         for it in range(n_iters):
@@ -156,6 +158,7 @@ def run(translate, angle, dims, Ms, box, mask, prior33=None, n_iters=200,
                 out["pred"][it] = pred.numpy()
                 out["etas"][it] = etas.numpy().ravel()
                 out["omegas"][it] = omegas.numpy().ravel()
+                out["ae"][it] = np.concatenate(surface_points.last_ae)
             opt.step()
             if record:
                 out["params"][it] = flat(leaves)

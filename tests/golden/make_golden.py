@@ -151,6 +151,17 @@ def main():
         assert np.array_equal(torch_oracle.points(rec["params"][-1], fast_sample_on_batch), rec["final_points"])
         for x, val in rec.items():
             out[f"c{k}_{x}"] = val
+        # the reference's discrete decisions per iteration (from the bit-identical torch restatement):
+        # arg-extreme sample per view/side, and the eta-grid bucket of every sample
+        out[f"c{k}_arg"] = t["arg"].astype(np.int16)
+        eta_idx = np.zeros((iters, 1000), np.uint8)
+        for it in range(iters):
+            o = c_oracle.sample(t["ae"][it, :3], t["ae"][it, 3:])
+            et = o["etas"].copy()
+            et[et == 0] += np.float32(1e-6)
+            assert np.array_equal(et, t["etas"][it])
+            eta_idx[it] = o["eta_idx"]
+        out[f"c{k}_eta_idx"] = eta_idx
         print(f"case {k}: obj {i} {rep} prior={pr} iters={iters} V={V}: loss {rec['loss'][0]:.4f} -> "
               f"{rec['loss'][-1]:.4f}; torch_oracle bit-identical")
     np.savez_compressed(os.path.join(OUT, "ref_runs.npz"), **out)
