@@ -154,6 +154,9 @@ def main():
         # the reference's discrete decisions per iteration (from the bit-identical torch restatement):
         # arg-extreme sample per view/side, and the eta-grid bucket of every sample
         out[f"c{k}_arg"] = t["arg"].astype(np.int16)
+        # ... and the sign of every residual pred - target (the L1 loss is non-smooth there: a residual within
+        # 1 ulp of zero flips the sign of that side's whole gradient contribution)
+        out[f"c{k}_resid_sign"] = np.sign(t["pred"] - scene.box[i][:V].astype(np.float32)[None]).astype(np.int8)
         eta_idx = np.zeros((iters, 1000), np.uint8)
         for it in range(iters):
             o = c_oracle.sample(t["ae"][it, :3], t["ae"][it, 3:])

@@ -33,7 +33,7 @@ class Case:
         self.prior_table = np.stack([G["prior_by_class"][c].astype(np.float32).reshape(9) for c in range(8)]) \
             if self.use_prior else None
         self.init = G[f"c{k}_init"]
-        for x in ("params", "grad", "m", "v", "loss", "final_points", "arg", "eta_idx"):
+        for x in ("params", "grad", "m", "v", "loss", "final_points", "arg", "eta_idx", "resid_sign"):
             setattr(self, x, G[f"c{k}_{x}"])
 
     def states_before(self):

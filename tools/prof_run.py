@@ -1,0 +1,41 @@
+"""Tiny driver for ncu captures: a few device-resident launches of the fused optimiser on a named config.
+
+    ncu --set full --clock-control none --import-source on -k regex:sq_optimize -s 1 -c 1 -o gpurun_out/prof \
+        python tools/prof_run.py --config 5 --objects 4736 --iters 20
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from odam_b200 import api, synthetic  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", type=int, default=2)
+ap.add_argument("--objects", type=int, default=None)
+ap.add_argument("--iters", type=int, default=None)
+ap.add_argument("--threads", type=int, default=0)
+ap.add_argument("--max-slices", type=int, default=0)
+ap.add_argument("--launches", type=int, default=2)
+a = ap.parse_args()
+c = synthetic.CONFIGS[a.config]
+scene = synthetic.make_scene(a.objects or c["n_objects"], c["n_views"], seed=a.config, device="cuda:0")
+tracks = api.pack_scene(scene)
+dt = api.DeviceTracks(tracks, "cuda:0", api.prior_table() if c["prior"] else None)
+iters = a.iters or c["n_iters"]
+out = None
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.launches + 1)]
+ev[0].record()
+for k in range(a.launches):
+    out = api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out)
+    ev[k + 1].record()
+torch.cuda.synchronize()
+units = float(tracks.total_views) * iters
+for k in range(a.launches):
+    ms = ev[k].elapsed_time(ev[k + 1])
+    print(f"launch {k}: {ms:.3f} ms  {units / ms / 1e3:.1f} M unit/s  "
+          f"{api.algorithmic_flops(tracks.view_off[1:] - tracks.view_off[:-1], iters) / ms / 1e9:.2f} TFLOP/s")
+print("flagged", int((out["status"].cpu() & 3 != 0).sum()))
