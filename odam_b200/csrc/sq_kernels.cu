@@ -56,7 +56,7 @@ struct OptArgs {
 };
 
 // phases A-D: parameters in S.par -> 1000 world points in S.px/py/pz (+ S.pj, grids)
-__device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads)
+__device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, bool have_prev)
 {
     const int warp = tid >> 5, lane = tid & 31;
     const int nwarps = nthreads >> 5;
@@ -70,7 +70,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads)
             P.e[k] = __fadd_rn(__fmul_rn(sg, 1.4f), 0.2f);
         }
         double sd, cd;
-        sincos((double)S.par[3], &sd, &cd);
+        sq_sincos_pi(S.par[3], sd, cd);  // yaw: correctly rounded cos/sin for |angle| < ~1e5 rad
         P.cz = (float)cd; P.sz = (float)sd;
         S.bad[0] = 0; S.bad[1] = 0;
     }
@@ -102,7 +102,12 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads)
         const Pose P = S.pose;
         for (int i = tid; i < kNPad; i += nthreads) {
             if (i < kN) {
-                int j = lower_bound_201(S.cdf, g_u_eta[i]);
+                // CDF bucket of this sample.  The bucket of the previous iteration is almost always still right;
+                // on the (monotone) CDF, "cdf[j-1] < u <= cdf[j]" is exactly what the bisection returns.
+                const float uu = g_u_eta[i];
+                int j = have_prev ? S.pj[i] : 0;
+                bool ok = have_prev && !(S.cdf[j] < uu) && (j == 0 || S.cdf[j - 1] < uu);
+                if (!ok) j = lower_bound_201(S.cdf, uu);
                 int k = g_k_omega[i];
                 float x0, y0, z0, X, Y, Z;
                 local_point(P, S.ge, S.go, j, k, x0, y0, z0);
@@ -126,12 +131,14 @@ __device__ __forceinline__ void load_M(const float *Ms, int gv, float (&M)[12])
     M[8] = r2.x; M[9] = r2.y; M[10] = r2.z; M[11] = r2.w;
 }
 
-// phase E for one (view, slice) item: extrema over chunks [c0, c1) and the arg index of each
+// phase E for one (view, slice) item: extrema over chunks [c0, c1) and, per side, the chunk that produced it
+// (-1 = no valid point improved on the +-1e6 sentinel).  The arg index is resolved later, only for the slice that
+// wins the cross-slice combine.
 __device__ __forceinline__ void scan_item(const Smem &S, const float (&M)[12], int c0, int c1,
-                                          float (&best)[4], int (&arg)[4])
+                                          float (&best)[4], int (&cid)[4])
 {
     best[0] = 1000000.f; best[1] = -1000000.f; best[2] = 1000000.f; best[3] = -1000000.f;
-    int cid[4] = {-1, -1, -1, -1};
+    cid[0] = cid[1] = cid[2] = cid[3] = -1;
     for (int c = c0; c < c1; c++) {
         const float4 *xs = reinterpret_cast<const float4 *>(S.px + c * kChunk);
         const float4 *ys = reinterpret_cast<const float4 *>(S.py + c * kChunk);
@@ -159,26 +166,24 @@ __device__ __forceinline__ void scan_item(const Smem &S, const float (&M)[12], i
         if (n2 < best[2]) { best[2] = n2; cid[2] = c; }
         if (n3 > best[3]) { best[3] = n3; cid[3] = c; }
     }
-    // resolve the index: first point of the recorded chunk whose (bit-identical) projection equals the extremum
+}
+
+// first point of chunk `c` whose projection (the bit-identical project_uv) equals the extremum `best`
+__device__ __forceinline__ int resolve_arg(const Smem &S, const float (&M)[12], int c, bool y_side, float best)
+{
+    int found = -1;
+    const int base = c * kChunk;
 #pragma unroll
-    for (int sd = 0; sd < 4; sd++) {
-        arg[sd] = -1;
-        if (cid[sd] >= 0) {
-            int base = cid[sd] * kChunk;
-            int found = -1;
-#pragma unroll
-            for (int h = kChunk - 1; h >= 0; h--) {
-                float u, w;
-                project_uv(M, S.px[base + h], S.py[base + h], S.pz[base + h], u, w);
-                if ((sd < 2 ? u : w) == best[sd]) found = base + h;
-            }
-            arg[sd] = found;
-        }
+    for (int h = kChunk - 1; h >= 0; h--) {
+        float u, w;
+        project_uv(M, S.px[base + h], S.py[base + h], S.pz[base + h], u, w);
+        if ((y_side ? w : u) == best) found = base + h;
     }
+    return found;
 }
 
 template <int kMaxThreads>
-__global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
+__global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_kernel(OptArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
     const float invV = V > 0 ? __fdiv_rn(1.f, (float)V) : 0.f;
 
     for (int it = 0; it < A.n_iters; it++) {
-        sample_surface(S, tid, T);
+        sample_surface(S, tid, T, it > 0);
         const bool last = it == A.n_iters - 1;
 
         // ---- E ----
@@ -218,10 +223,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
             load_M(A.Ms, v_begin + v, M);
             int c0 = (sl * kNChunks) / slices, c1 = ((sl + 1) * kNChunks) / slices;
             float best[4];
-            int arg[4];
-            scan_item(S, M, c0, c1, best, arg);
-#pragma unroll
-            for (int sd = 0; sd < 4; sd++) { ext_val[item * 4 + sd] = best[sd]; ext_arg[item * 4 + sd] = arg[sd]; }
+            int cid[4];
+            scan_item(S, M, c0, c1, best, cid);
+            reinterpret_cast<float4 *>(ext_val)[item] = make_float4(best[0], best[1], best[2], best[3]);
+            reinterpret_cast<int4 *>(ext_arg)[item] = make_int4(cid[0], cid[1], cid[2], cid[3]);
         }
         __syncthreads();
 
@@ -230,15 +235,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
 #pragma unroll
         for (int k = 0; k < kRed; k++) acc[k] = 0.f;
         const Pose P = S.pose;
+        float lside = 0.f;               // this thread's side is fixed: sd = tid & 3 (T is a multiple of 4)
+        const int sd = tid & 3;
         for (int pr = tid; pr < 4 * V; pr += T) {
-            int v = pr >> 2, sd = pr & 3;
+            int v = pr >> 2;
             // combine slices in index order; strict comparison keeps the first index on ties
             float best = ext_val[v * 4 + sd];
-            int arg = ext_arg[v * 4 + sd];
+            int cid = ext_arg[v * 4 + sd];
             for (int sl = 1; sl < slices; sl++) {
                 float b = ext_val[(sl * V + v) * 4 + sd];
                 bool better = (sd & 1) ? (b > best) : (b < best);
-                if (better) { best = b; arg = ext_arg[(sl * V + v) * 4 + sd]; }
+                if (better) { best = b; cid = ext_arg[(sl * V + v) * 4 + sd]; }
             }
             int gv = v_begin + v;
             float target = A.box[(size_t)gv * 4 + sd];
@@ -248,8 +255,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
             // loss carries the same fp32 noise as the reference's instead of an independent sample of it.
             float M[12];
             float qx = 0.f, qy = 0.f, qz = 1.f, d = 1.f;
-            if (arg >= 0) {
+            int arg = -1;
+            if (cid >= 0) {
                 load_M(A.Ms, gv, M);
+                arg = resolve_arg(S, M, cid, sd >= 2, best);
+            }
+            if (arg >= 0) {
                 float X = S.px[arg], Y = S.py[arg], Z = S.pz[arg];
                 qx = __fadd_rn(__fmaf_rn(Z, M[2], __fmaf_rn(Y, M[1], __fmul_rn(X, M[0]))), M[3]);
                 qy = __fadd_rn(__fmaf_rn(Z, M[6], __fmaf_rn(Y, M[5], __fmul_rn(X, M[4]))), M[7]);
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
             float diff = __fsub_rn(best, target);
             float l = fabsf(diff);
             if (!(l == l)) l = 0.f;  // sq_libs.py:426-427
-            acc[9 + sd] = __fadd_rn(acc[9 + sd], __fmul_rn(l, mk));
+            lside = __fadd_rn(lside, __fmul_rn(l, mk));
             if (last) {
                 if (A.out_pred) A.out_pred[(size_t)gv * 4 + sd] = best;
                 if (A.out_arg) A.out_arg[(size_t)gv * 4 + sd] = arg;
@@ -272,10 +283,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
             float num = sd < 2 ? qx : qy;
             float g_lin = __fdiv_rn(c, d);                                        // d(u)/d(q_x or q_y)
             float g_z = -__fmul_rn(__fdiv_rn(__fmul_rn(c, num), __fmul_rn(d, d)), sgnf(qz));  // d(u)/d(q_z)
-            int r0 = sd < 2 ? 0 : 4;
-            float gp0 = __fmaf_rn(M[8], g_z, __fmul_rn(M[r0 + 0], g_lin));
-            float gp1 = __fmaf_rn(M[9], g_z, __fmul_rn(M[r0 + 1], g_lin));
-            float gp2 = __fmaf_rn(M[10], g_z, __fmul_rn(M[r0 + 2], g_lin));
+            float gp0 = __fmaf_rn(M[8], g_z, __fmul_rn(sd < 2 ? M[0] : M[4], g_lin));
+            float gp1 = __fmaf_rn(M[9], g_z, __fmul_rn(sd < 2 ? M[1] : M[5], g_lin));
+            float gp2 = __fmaf_rn(M[10], g_z, __fmul_rn(sd < 2 ? M[2] : M[6], g_lin));
             int j = S.pj[arg], k = g_k_omega[arg];
             float x0, y0, z0;
             local_point(P, S.ge, S.go, j, k, x0, y0, z0);
@@ -302,6 +312,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sq_optimize_kernel(OptArgs A)
             }
         }
         // ---- G: deterministic reduction (butterfly inside the warp, warp order across) ----
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[9 + k] = sd == k ? lside : 0.f;
 #pragma unroll
         for (int k = 0; k < kRed; k++) {
             float x = acc[k];
@@ -393,7 +405,7 @@ __global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int
     const int tid = threadIdx.x, obj = blockIdx.x;
     if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
     __syncthreads();
-    sample_surface(S, tid, blockDim.x);
+    sample_surface(S, tid, blockDim.x, false);
     for (int i = tid; i < kN; i += blockDim.x) {
         float *o = out_xyz + ((size_t)obj * kN + i) * 3;
         o[0] = S.px[i]; o[1] = S.py[i]; o[2] = S.pz[i];
@@ -434,7 +446,7 @@ __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, cons
     const int tid = threadIdx.x, obj = blockIdx.x;
     if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
     __syncthreads();
-    sample_surface(S, tid, blockDim.x);
+    sample_surface(S, tid, blockDim.x, false);
     const int v_begin = view_off[obj], V = view_off[obj + 1] - v_begin;
     for (int v = tid; v < V; v += blockDim.x) {
         float M[12];
@@ -542,6 +554,7 @@ static int ensure_init(int device)
     CU(cudaMemcpyToSymbol(g_u_eta, u.data(), sizeof(float) * kN));
     CU(cudaMemcpyToSymbol(g_k_omega, kom.data(), kN));
     CU(cudaFuncSetAttribute(sq_optimize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
+    CU(cudaFuncSetAttribute(sq_optimize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
     CU(cudaFuncSetAttribute(sq_optimize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
     CU(cudaFuncSetAttribute(sq_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
     CU(cudaFuncSetAttribute(sq_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
@@ -595,7 +608,9 @@ static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L
     OptArgs A = A0;
     A.max_slices = L.max_slices;
     A.beta1w = (float)(1.0 - 0.9); A.beta2 = (float)0.999; A.beta2w = (float)(1.0 - 0.999); A.eps = (float)1e-8;
+    // every instantiation is capped at 64 registers/thread (1024 resident threads per SM worth of registers)
     if (L.threads <= 256) sq_optimize_kernel<256><<<A.n, L.threads, L.smem, st>>>(A);
+    else if (L.threads <= 512) sq_optimize_kernel<512><<<A.n, L.threads, L.smem, st>>>(A);
     else sq_optimize_kernel<1024><<<A.n, L.threads, L.smem, st>>>(A);
     CU(cudaGetLastError());
     return ODAM_SQ_OK;
