@@ -82,7 +82,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
         const Pose &P = S.pose;
         if (warp == 0) {
             int bad = 0;
-            build_grid_warp(S.ge, S.queue[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, lane, bad);  // :183-190
+            build_grid_warp(S.ge, S.queue[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);  // :183-190
             build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                        // :191-199
             __syncwarp();
             patch_zero_angle(S.ge, P.e[0], lane);
@@ -90,7 +90,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
         }
         if (warp == (nwarps > 1 ? 1 : 0)) {
             int bad = 0;
-            build_grid_warp(S.go, S.queue[1], P.a[0], P.a[1], P.e[1], pi, -pi, lane, bad);      // :202-209
+            build_grid_warp(S.go, S.queue[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad);  // :202-209
             __syncwarp();
             patch_zero_angle(S.go, P.e[1], lane);
             if (bad) S.bad[1] = 1;
@@ -105,8 +105,19 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
                 // CDF bucket of this sample.  The bucket of the previous iteration is almost always still right;
                 // on the (monotone) CDF, "cdf[j-1] < u <= cdf[j]" is exactly what the bisection returns.
                 const float uu = g_u_eta[i];
-                int j = have_prev ? S.pj[i] : 0;
-                bool ok = have_prev && !(S.cdf[j] < uu) && (j == 0 || S.cdf[j - 1] < uu);
+                int j;
+                bool ok = false;
+                if (have_prev) {  // walk at most 3 buckets from last iteration's answer
+                    j = S.pj[i];
+#pragma unroll
+                    for (int w = 0; w < 3; w++) {
+                        bool up = S.cdf[j] < uu;
+                        bool down = j > 0 && !(S.cdf[j - 1] < uu);
+                        j += up ? 1 : (down ? -1 : 0);
+                        j = min(j, kG - 1);
+                    }
+                    ok = !(S.cdf[j] < uu) && (j == 0 || S.cdf[j - 1] < uu);
+                }
                 if (!ok) j = lower_bound_201(S.cdf, uu);
                 int k = g_k_omega[i];
                 float x0, y0, z0, X, Y, Z;
@@ -300,11 +311,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             acc[5] += 2.f * S.par[5] * (gl1 * fce * fso);
             acc[6] += 2.f * S.par[6] * (gl2 * fse);
             if (A.optimize_shapes) {
-                float eta = S.ge.th[j], om = S.go.th[k];
-                if (eta == 0.f) eta = 1e-6f;
-                if (om == 0.f) om = 1e-6f;
-                float lce = logf(fabsf(cosf(eta))), lse = logf(fabsf(sinf(eta)));
-                float lco = logf(fabsf(cosf(om))), lso = logf(fabsf(sinf(om)));
+                float lce = S.ge.lc[j], lse = S.ge.ls[j], lco = S.go.lc[k], lso = S.go.ls[k];
                 float ge1 = (gl0 * x0 + gl1 * y0) * lce + gl2 * z0 * lse;
                 float ge2 = gl0 * x0 * lco + gl1 * y0 * lso;
                 acc[7] += ge1 * 1.4f * P.sig[0] * (1.f - P.sig[0]);
@@ -424,10 +431,10 @@ __global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const flo
     const float e1 = e[obj * 2 + 0], e2 = e[obj * 2 + 1];
     int bad = 0;
     if (warp == 0) {
-        build_grid_warp(S.ge, S.queue[0], a1, a3, e1, pi_2, -pi_2, lane, bad);
+        build_grid_warp(S.ge, S.queue[0], a1, a3, e1, pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);
         build_cdf_warp(S.ge, S.cdf, __fadd_rn(a1, a2), lane);
     } else {
-        build_grid_warp(S.go, S.queue[1], a1, a2, e2, pi, -pi, lane, bad);
+        build_grid_warp(S.go, S.queue[1], a1, a2, e2, pi, -pi, g_logtab[1], pi_2, lane, bad);
     }
     __syncthreads();
     for (int i = tid; i < kN; i += blockDim.x) {
@@ -519,6 +526,18 @@ static void host_uniforms(uint32_t seed, int n, float *out)
     }
 }
 
+// log|cosf(theta)|, log|sinf(theta)| at the dyadic angles of a D&C tree rooted at (ta, tb); heap-indexed.
+static void gen_logtab(float ta, float tb, int pos, std::vector<double2> &tab)
+{
+    if (pos >= kTabSize) return;
+    const float th = (ta + tb) * 0.5f;
+    const float c = (float)cosl((long double)th), s = (float)sinl((long double)th);
+    tab[pos].x = (double)logl(fabsl((long double)c));
+    tab[pos].y = s == 0.f ? -1e300 : (double)logl(fabsl((long double)s));
+    gen_logtab(ta, th, 2 * pos, tab);
+    gen_logtab(th, tb, 2 * pos + 1, tab);
+}
+
 struct DeviceState {
     bool ready = false;
     int sm_count = 0;
@@ -553,6 +572,16 @@ static int ensure_init(int device)
     for (int i = 0; i < kN; i++) kom[i] = (uint8_t)(int)(u[kN + i] * (float)kG);  // sampling.cpp:211
     CU(cudaMemcpyToSymbol(g_u_eta, u.data(), sizeof(float) * kN));
     CU(cudaMemcpyToSymbol(g_k_omega, kom.data(), kN));
+    {
+        const float pi = 3.14159274101257324f, pi_2 = pi * 0.5f;
+        std::vector<double2> tab(2 * kTabSize, make_double2(0.0, 0.0));
+        std::vector<double2> one(kTabSize, make_double2(0.0, 0.0));
+        gen_logtab(pi_2, -pi_2, 1, one);
+        std::copy(one.begin(), one.end(), tab.begin());
+        gen_logtab(pi, -pi, 1, one);
+        std::copy(one.begin(), one.end(), tab.begin() + kTabSize);
+        CU(cudaMemcpyToSymbol(g_logtab, tab.data(), sizeof(double2) * 2 * kTabSize));
+    }
     CU(cudaFuncSetAttribute(sq_optimize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
     CU(cudaFuncSetAttribute(sq_optimize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
     CU(cudaFuncSetAttribute(sq_optimize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));

@@ -89,9 +89,34 @@ SQ_HD void sq_sincos_pi(float theta, double &s, double &c)
     }
 }
 
+// exp(y) for -700 < y <= 0:  y = k ln2 + r, |r| <= ln2/2, Taylor to r^13, scaled by 2^k through the exponent field
+SQ_HD double sq_exp_neg(double y)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double kf = rint(y * 1.44269504088896338700e+00);
+    double r = sq_fma(-kf, ln2_hi, y);
+    r = sq_fma(-kf, ln2_lo, r);
+    double e = 1.0 / 6227020800.0;
+    e = sq_fma(e, r, 1.0 / 479001600.0);
+    e = sq_fma(e, r, 1.0 / 39916800.0);
+    e = sq_fma(e, r, 1.0 / 3628800.0);
+    e = sq_fma(e, r, 1.0 / 362880.0);
+    e = sq_fma(e, r, 1.0 / 40320.0);
+    e = sq_fma(e, r, 1.0 / 5040.0);
+    e = sq_fma(e, r, 1.0 / 720.0);
+    e = sq_fma(e, r, 1.0 / 120.0);
+    e = sq_fma(e, r, 1.0 / 24.0);
+    e = sq_fma(e, r, 1.0 / 6.0);
+    e = sq_fma(e, r, 0.5);
+    e = sq_fma(e, r, 1.0);
+    e = sq_fma(e, r, 1.0);
+    const int k = (int)kf;  // never subnormal on the caller's domain
+    return sq_bits_to_double(sq_double_to_bits(e) + ((uint64_t)(int64_t)k << 52));
+}
+
 // x^p for 0 <= x <= 1 (float), 0 < p < 2 (float); exp(p * log(x)) in double:
 //   log:  x = 2^E * m, m in [sqrt(.5), sqrt(2));  log m = 2 atanh(s), s = (m-1)/(m+1), odd series to s^17
-//   exp:  y = k ln2 + r, |r| <= ln2/2, Taylor to r^13, scaled by 2^k through the exponent field
+//   exp:  sq_exp_neg
 SQ_HD double sq_pow01(float xf, float pf)
 {
     if (xf == 0.0f) return 0.0;
@@ -116,26 +141,7 @@ SQ_HD double sq_pow01(float xf, float pf)
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double dE = (double)E;
     const double lx = sq_fma(dE, ln2_hi, sq_fma(dE, ln2_lo, lm));  // log(x) <= 0
-    const double y = (double)pf * lx;
-    const double kf = rint(y * 1.44269504088896338700e+00);
-    double r = sq_fma(-kf, ln2_hi, y);
-    r = sq_fma(-kf, ln2_lo, r);
-    double e = 1.0 / 6227020800.0;
-    e = sq_fma(e, r, 1.0 / 479001600.0);
-    e = sq_fma(e, r, 1.0 / 39916800.0);
-    e = sq_fma(e, r, 1.0 / 3628800.0);
-    e = sq_fma(e, r, 1.0 / 362880.0);
-    e = sq_fma(e, r, 1.0 / 40320.0);
-    e = sq_fma(e, r, 1.0 / 5040.0);
-    e = sq_fma(e, r, 1.0 / 720.0);
-    e = sq_fma(e, r, 1.0 / 120.0);
-    e = sq_fma(e, r, 1.0 / 24.0);
-    e = sq_fma(e, r, 1.0 / 6.0);
-    e = sq_fma(e, r, 0.5);
-    e = sq_fma(e, r, 1.0);
-    e = sq_fma(e, r, 1.0);
-    const int k = (int)kf;  // -95 .. 0 on this domain: never subnormal
-    return sq_bits_to_double(sq_double_to_bits(e) + ((uint64_t)(int64_t)k << 52));
+    return sq_exp_neg((double)pf * lx);
 }
 
 // sign(c) * |c|^p as the reference's fexp (sampling.cpp:59-61), float in / float out
