@@ -60,19 +60,21 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
 {
     const int warp = tid >> 5, lane = tid & 31;
     const int nwarps = nthreads >> 5;
-    // ---- A ----
-    if (tid == 0) {
+    // ---- A ---- (six lanes, one derived quantity each)
+    {
         Pose &P = S.pose;
-        for (int k = 0; k < 3; k++) { P.a[k] = __fmul_rn(S.par[4 + k], S.par[4 + k]); P.t[k] = S.par[k]; }
-        for (int k = 0; k < 2; k++) {
+        if (tid < 3) { P.a[tid] = __fmul_rn(S.par[4 + tid], S.par[4 + tid]); P.t[tid] = S.par[tid]; }
+        else if (tid < 5) {
+            const int k = tid - 3;
             float sg = (float)(1.0 / (1.0 + exp(-(double)S.par[7 + k])));  // torch.sigmoid, correctly rounded
             P.sig[k] = sg;
             P.e[k] = __fadd_rn(__fmul_rn(sg, 1.4f), 0.2f);
+        } else if (tid == 5) {
+            double sd, cd;
+            sq_sincos_pi(S.par[3], sd, cd);  // yaw: correctly rounded cos/sin for |angle| < ~1e5 rad
+            P.cz = (float)cd; P.sz = (float)sd;
+            S.bad[0] = 0; S.bad[1] = 0;
         }
-        double sd, cd;
-        sq_sincos_pi(S.par[3], sd, cd);  // yaw: correctly rounded cos/sin for |angle| < ~1e5 rad
-        P.cz = (float)cd; P.sz = (float)sd;
-        S.bad[0] = 0; S.bad[1] = 0;
     }
     __syncthreads();
     // ---- B, C ----
@@ -105,18 +107,18 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
                 // CDF bucket of this sample.  The bucket of the previous iteration is almost always still right;
                 // on the (monotone) CDF, "cdf[j-1] < u <= cdf[j]" is exactly what the bisection returns.
                 const float uu = g_u_eta[i];
-                int j;
+                int j = 0;
                 bool ok = false;
-                if (have_prev) {  // walk at most 3 buckets from last iteration's answer
+                if (have_prev) {
                     j = S.pj[i];
-#pragma unroll
-                    for (int w = 0; w < 3; w++) {
-                        bool up = S.cdf[j] < uu;
-                        bool down = j > 0 && !(S.cdf[j - 1] < uu);
-                        j += up ? 1 : (down ? -1 : 0);
-                        j = min(j, kG - 1);
+                    float hi = S.cdf[j], lo = j > 0 ? S.cdf[j - 1] : -1.f;
+                    bool up = hi < uu, down = !(lo < uu);
+                    ok = !up && !down;
+                    if (__any_sync(__activemask(), !ok)) {  // most moves are to a neighbouring bucket
+                        int j1 = min(max(j + (up ? 1 : (down ? -1 : 0)), 0), kG - 1);
+                        float hi1 = S.cdf[j1], lo1 = j1 > 0 ? S.cdf[j1 - 1] : -1.f;
+                        if (!ok && !(hi1 < uu) && lo1 < uu) { j = j1; ok = true; }
                     }
-                    ok = !(S.cdf[j] < uu) && (j == 0 || S.cdf[j - 1] < uu);
                 }
                 if (!ok) j = lower_bound_201(S.cdf, uu);
                 int k = g_k_omega[i];
@@ -321,21 +323,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         // ---- G: deterministic reduction (butterfly inside the warp, warp order across) ----
 #pragma unroll
         for (int k = 0; k < 4; k++) acc[9 + k] = sd == k ? lside : 0.f;
+        const int nred = min(nwarps, (4 * V + 31) >> 5);  // warps that had (view, side) pairs
+        if (warp < nred) {
 #pragma unroll
-        for (int k = 0; k < kRed; k++) {
-            float x = acc[k];
+            for (int k = 0; k < kRed; k++) {
+                float x = acc[k];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
-            acc[k] = x;
-        }
-        if (lane == 0) {
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+                acc[k] = x;
+            }
+            if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < kRed; k++) S.red[warp][k] = acc[k];
+                for (int k = 0; k < kRed; k++) S.red[warp][k] = acc[k];
+            }
         }
         __syncthreads();
         if (tid < kRed) {
             float x = 0.f;
-            for (int wi = 0; wi < nwarps; wi++) x += S.red[wi][tid];
+            for (int wi = 0; wi < nred; wi++) x += S.red[wi][tid];
             S.red[0][tid] = x;
         }
         __syncthreads();
@@ -576,9 +581,15 @@ static int ensure_init(int device)
         const float pi = 3.14159274101257324f, pi_2 = pi * 0.5f;
         std::vector<double2> tab(2 * kTabSize, make_double2(0.0, 0.0));
         std::vector<double2> one(kTabSize, make_double2(0.0, 0.0));
+        auto endpoint = [](float th) {
+            const float c = (float)cosl((long double)th), s = (float)sinl((long double)th);
+            return make_double2((double)logl(fabsl((long double)c)), (double)logl(fabsl((long double)s)));
+        };
         gen_logtab(pi_2, -pi_2, 1, one);
+        one[0] = endpoint(pi_2);
         std::copy(one.begin(), one.end(), tab.begin());
         gen_logtab(pi, -pi, 1, one);
+        one[0] = endpoint(pi);
         std::copy(one.begin(), one.end(), tab.begin() + kTabSize);
         CU(cudaMemcpyToSymbol(g_logtab, tab.data(), sizeof(double2) * 2 * kTabSize));
     }
