@@ -213,7 +213,7 @@ class DeviceTracks:
 
 
 def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr_shape=0.1, threads=0,
-                    max_slices=0, out=None):
+                    max_slices=0, out=None, cycles=None):
     """Enqueue one fused launch on torch's current stream; returns dict of CUDA tensors (no sync)."""
     torch = dt.torch
     L = _lib.load()
@@ -229,6 +229,8 @@ def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr
         threads = th.value
     o.threads, o.max_slices = int(threads), int(max_slices)
     o.max_views = int(np.diff(dt.view_off_host).max()) if dt.n else 0
+    if cycles is not None:  # int64 CUDA tensor [n, 8]: per-phase SM cycles (diagnostics)
+        o.out_cycles = cycles.data_ptr()
     p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
     with torch.cuda.device(dt.device):
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)

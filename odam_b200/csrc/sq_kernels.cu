@@ -41,7 +41,17 @@ struct alignas(16) Smem {
     Pose pose;
     int status;
     int bad[2];
+    long long tmark, cyc[8];                // per-phase clock64() accumulation by thread 0 (diagnostics)
 };
+
+#define SQ_MARK(S, tid, k)                                                \
+    do {                                                                   \
+        if ((tid) == 0) {                                                  \
+            long long now_ = clock64();                                    \
+            (S).cyc[k] += now_ - (S).tmark;                                \
+            (S).tmark = now_;                                              \
+        }                                                                  \
+    } while (0)
 
 struct OptArgs {
     const float *init; const int32_t *cls; const int32_t *view_off;
@@ -53,6 +63,7 @@ struct OptArgs {
     float *out_params, *out_loss; int32_t *out_status;
     float *out_m, *out_v, *out_grad, *out_pred; int32_t *out_arg; uint8_t *out_eta_idx; float *out_grids;
     float *out_param_hist;
+    long long *out_cycles;
 };
 
 // phases A-D: parameters in S.par -> 1000 world points in S.px/py/pz (+ S.pj, grids)
@@ -77,6 +88,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
         }
     }
     __syncthreads();
+    SQ_MARK(S, tid, 0);
     // ---- B, C ----
     const float pi = 3.14159274101257324f;       // (float)acos(-1), sampling.cpp:14
     const float pi_2 = __fmul_rn(pi, 0.5f);      // pi/2, :15
@@ -99,6 +111,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
         }
     }
     __syncthreads();
+    SQ_MARK(S, tid, 1);
     // ---- D ----
     {
         const Pose P = S.pose;
@@ -133,6 +146,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
         }
     }
     __syncthreads();
+    SQ_MARK(S, tid, 2);
 }
 
 __device__ __forceinline__ void load_M(const float *Ms, int gv, float (&M)[12])
@@ -220,7 +234,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         if (A.prior) S.prior[tid] = A.prior[(size_t)A.cls[obj] * 9 + tid];
     }
     if (tid < 3) S.s0[tid] = A.s0 ? A.s0[(size_t)obj * 3 + tid] : A.init[(size_t)obj * 9 + 4 + tid];
-    if (tid == 0) S.status = 0;
+    if (tid == 0) {
+        S.status = 0;
+        for (int k = 0; k < 8; k++) S.cyc[k] = 0;
+        S.tmark = clock64();
+    }
     __syncthreads();
 
     const float invV = V > 0 ? __fdiv_rn(1.f, (float)V) : 0.f;
@@ -242,6 +260,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             reinterpret_cast<int4 *>(ext_arg)[item] = make_int4(cid[0], cid[1], cid[2], cid[3]);
         }
         __syncthreads();
+        SQ_MARK(S, tid, 3);
 
         // ---- F ----
         float acc[kRed];
@@ -338,6 +357,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             }
         }
         __syncthreads();
+        SQ_MARK(S, tid, 4);
         if (tid < kRed) {
             float x = 0.f;
             for (int wi = 0; wi < nred; wi++) x += S.red[wi][tid];
@@ -373,6 +393,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             if (S.bad[0] | S.bad[1]) S.status |= ODAM_SQ_ST_SAMPLER;
         }
         __syncthreads();
+        SQ_MARK(S, tid, 5);
         // Adam (torch/optim/adam.py _single_tensor_adam; roundings as probed against torch's CPU kernels)
         if (tid < (A.optimize_shapes ? 9 : 7)) {
             float g = S.grad[tid], m = S.m[tid], v = S.v[tid], p = S.par[tid];
@@ -396,7 +417,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             }
         }
         __syncthreads();
+        SQ_MARK(S, tid, 6);
     }
+    if (A.out_cycles && tid < 8) A.out_cycles[(size_t)obj * 8 + tid] = S.cyc[tid];
     if (tid < 9) {
         float p = S.par[tid];
         A.out_params[(size_t)obj * 9 + tid] = p;
@@ -781,6 +804,7 @@ int odam_sq_optimize(const float *init, const int32_t *cls, const int32_t *view_
         A.out_m = opt->out_m; A.out_v = opt->out_v; A.out_grad = opt->out_grad; A.out_pred = opt->out_pred;
         A.out_arg = opt->out_arg; A.out_eta_idx = opt->out_eta_idx; A.out_grids = opt->out_grids;
         A.out_param_hist = opt->out_param_hist;
+        A.out_cycles = (long long *)opt->out_cycles;
     }
     return launch_optimize(D, A, L, st);
 }

@@ -20,6 +20,7 @@ ap.add_argument("--iters", type=int, default=None)
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--max-slices", type=int, default=0)
 ap.add_argument("--launches", type=int, default=2)
+ap.add_argument("--cycles", action="store_true")
 a = ap.parse_args()
 c = synthetic.CONFIGS[a.config]
 scene = synthetic.make_scene(a.objects or c["n_objects"], c["n_views"], seed=a.config, device="cuda:0")
@@ -39,3 +40,13 @@ for k in range(a.launches):
     print(f"launch {k}: {ms:.3f} ms  {units / ms / 1e3:.1f} M unit/s  "
           f"{api.algorithmic_flops(tracks.view_off[1:] - tracks.view_off[:-1], iters) / ms / 1e9:.2f} TFLOP/s")
 print("flagged", int((out["status"].cpu() & 3 != 0).sum()))
+if a.cycles:
+    cyc = torch.zeros((tracks.n, 8), dtype=torch.int64, device="cuda:0")
+    api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc)
+    torch.cuda.synchronize()
+    c = cyc.cpu().numpy().astype(float) / iters
+    names = ["A derive", "B/C grids+cdf", "D points", "E project", "F backward", "G reduce+loss", "Adam", "-"]
+    print("mean SM cycles per iteration per object (thread 0's view):")
+    for k in range(7):
+        print(f"  {names[k]:14s} {c[:, k].mean():9.0f}  ({c[:, k].mean() / c[:, :7].sum(1).mean():5.1%})")
+    print(f"  total          {c[:, :7].sum(1).mean():9.0f}")
