@@ -34,7 +34,6 @@ struct alignas(16) Smem {
     float px[kNPad], py[kNPad], pz[kNPad];  // world points, SoA
     GridTab ge, go;
     float cdf[kGPad];
-    int queue[2][kGPad];
     uint8_t pj[kNPad];                      // eta-grid index of each sample
     float red[kMaxWarps][kRed + 3];
     float par[12], m[12], v[12], s0[4], grad[12], prior[12];
@@ -89,22 +88,29 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
     }
     __syncthreads();
     SQ_MARK(S, tid, 0);
-    // ---- B, C ----
+    // ---- B0: pre-evaluate last iteration's nodes with the new exponents (all threads) ----
     const float pi = 3.14159274101257324f;       // (float)acos(-1), sampling.cpp:14
     const float pi_2 = __fmul_rn(pi, 0.5f);      // pi/2, :15
+    if (have_prev) {
+        // interleave the two grids so that every warp gets a share of both
+        speculate_nodes(S.ge, S.pose.e[0], g_logtab[0], pi_2, tid, nthreads);
+        speculate_nodes(S.go, S.pose.e[1], g_logtab[1], pi_2, nthreads - 1 - tid, nthreads);
+        __syncthreads();
+    }
+    // ---- B, C ----
     {
         const Pose &P = S.pose;
         if (warp == 0) {
             int bad = 0;
-            build_grid_warp(S.ge, S.queue[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);  // :183-190
-            build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                        // :191-199
+            build_grid_warp(S.ge, P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, have_prev, lane, bad);  // :183-190
+            build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                                        // :191-199
             __syncwarp();
             patch_zero_angle(S.ge, P.e[0], lane);
             if (bad) S.bad[0] = 1;
         }
         if (warp == (nwarps > 1 ? 1 : 0)) {
             int bad = 0;
-            build_grid_warp(S.go, S.queue[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad);  // :202-209
+            build_grid_warp(S.go, P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, have_prev, lane, bad);     // :202-209
             __syncwarp();
             patch_zero_angle(S.go, P.e[1], lane);
             if (bad) S.bad[1] = 1;
@@ -332,7 +338,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             acc[5] += 2.f * S.par[5] * (gl1 * fce * fso);
             acc[6] += 2.f * S.par[6] * (gl2 * fse);
             if (A.optimize_shapes) {
-                float lce = S.ge.lc[j], lse = S.ge.ls[j], lco = S.go.lc[k], lso = S.go.ls[k];
+                float lce, lse, lco, lso;
+                slot_logs(S.ge, j, g_logtab[0], lce, lse);
+                slot_logs(S.go, k, g_logtab[1], lco, lso);
                 float ge1 = (gl0 * x0 + gl1 * y0) * lce + gl2 * z0 * lse;
                 float ge2 = gl0 * x0 * lco + gl1 * y0 * lso;
                 acc[7] += ge1 * 1.4f * P.sig[0] * (1.f - P.sig[0]);
@@ -459,10 +467,10 @@ __global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const flo
     const float e1 = e[obj * 2 + 0], e2 = e[obj * 2 + 1];
     int bad = 0;
     if (warp == 0) {
-        build_grid_warp(S.ge, S.queue[0], a1, a3, e1, pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);
+        build_grid_warp(S.ge, a1, a3, e1, pi_2, -pi_2, g_logtab[0], pi_2, false, lane, bad);
         build_cdf_warp(S.ge, S.cdf, __fadd_rn(a1, a2), lane);
     } else {
-        build_grid_warp(S.go, S.queue[1], a1, a2, e2, pi, -pi, g_logtab[1], pi_2, lane, bad);
+        build_grid_warp(S.go, a1, a2, e2, pi, -pi, g_logtab[1], pi_2, false, lane, bad);
     }
     __syncthreads();
     for (int i = tid; i < kN; i += blockDim.x) {

@@ -114,12 +114,10 @@ SQ_HD double sq_exp_neg(double y)
     return sq_bits_to_double(sq_double_to_bits(e) + ((uint64_t)(int64_t)k << 52));
 }
 
-// x^p for 0 <= x <= 1 (float), 0 < p < 2 (float); exp(p * log(x)) in double:
-//   log:  x = 2^E * m, m in [sqrt(.5), sqrt(2));  log m = 2 atanh(s), s = (m-1)/(m+1), odd series to s^17
-//   exp:  sq_exp_neg
-SQ_HD double sq_pow01(float xf, float pf)
+// log(x) for a float 0 < x <= 1, in double:  x = 2^E * m, m in [sqrt(.5), sqrt(2));
+// log m = 2 atanh(s), s = (m-1)/(m+1), odd series to s^17
+SQ_HD double sq_log01(float xf)
 {
-    if (xf == 0.0f) return 0.0;
     const double x = (double)xf;
     uint64_t ux = sq_double_to_bits(x);
     int E = (int)((ux >> 52) & 0x7ff) - 1023;
@@ -140,8 +138,14 @@ SQ_HD double sq_pow01(float xf, float pf)
     const double lm = sq_fma(2.0 * s * z, q, 2.0 * s);          // log(m)
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double dE = (double)E;
-    const double lx = sq_fma(dE, ln2_hi, sq_fma(dE, ln2_lo, lm));  // log(x) <= 0
-    return sq_exp_neg((double)pf * lx);
+    return sq_fma(dE, ln2_hi, sq_fma(dE, ln2_lo, lm));
+}
+
+// x^p for 0 <= x <= 1 (float), 0 < p < 2 (float): exp(p * log(x)) in double
+SQ_HD double sq_pow01(float xf, float pf)
+{
+    if (xf == 0.0f) return 0.0;
+    return sq_exp_neg((double)pf * sq_log01(xf));
 }
 
 // sign(c) * |c|^p as the reference's fexp (sampling.cpp:59-61), float in / float out
