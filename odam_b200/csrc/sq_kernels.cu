@@ -52,6 +52,9 @@ struct alignas(16) Smem {
         }                                                                  \
     } while (0)
 
+constexpr size_t kSpecBytes = 2 * sizeof(GridSpec);
+constexpr size_t kFwdSmem = sizeof(Smem) + kSpecBytes;  // forward-only kernels: fixed part + B0 scratch
+
 struct OptArgs {
     const float *init; const int32_t *cls; const int32_t *view_off;
     const float *Ms; const float *box; const uint8_t *mask; const float *prior;
@@ -66,7 +69,7 @@ struct OptArgs {
 };
 
 // phases A-D: parameters in S.par -> 1000 world points in S.px/py/pz (+ S.pj, grids)
-__device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, bool have_prev)
+__device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid, int nthreads, bool have_prev)
 {
     const int warp = tid >> 5, lane = tid & 31;
     const int nwarps = nthreads >> 5;
@@ -88,29 +91,37 @@ __device__ __forceinline__ void sample_surface(Smem &S, int tid, int nthreads, b
     }
     __syncthreads();
     SQ_MARK(S, tid, 0);
-    // ---- B0: pre-evaluate last iteration's nodes with the new exponents (all threads) ----
+    // ---- B0: everything about the previous tree's nodes that does not depend on slot counts (all threads) ----
     const float pi = 3.14159274101257324f;       // (float)acos(-1), sampling.cpp:14
     const float pi_2 = __fmul_rn(pi, 0.5f);      // pi/2, :15
-    if (have_prev) {
-        // interleave the two grids so that every warp gets a share of both
-        speculate_nodes(S.ge, S.pose.e[0], g_logtab[0], pi_2, tid, nthreads);
-        speculate_nodes(S.go, S.pose.e[1], g_logtab[1], pi_2, nthreads - 1 - tid, nthreads);
+    {
+        const Pose &P = S.pose;
+        // the two grids are interleaved from opposite ends so that every warp gets a share of both
+        spec_powers(S.ge, spec[0], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, have_prev, tid, nthreads);
+        spec_powers(S.go, spec[1], P.e[1], pi, -pi, g_logtab[1], pi_2, have_prev, nthreads - 1 - tid, nthreads);
         __syncthreads();
+        if (have_prev) {
+            spec_ratios(S.ge, spec[0], P.a[0], P.a[2], true, tid, nthreads);
+            spec_ratios(S.go, spec[1], P.a[0], P.a[1], true, nthreads - 1 - tid, nthreads);
+            __syncthreads();
+        }
     }
     // ---- B, C ----
     {
         const Pose &P = S.pose;
         if (warp == 0) {
             int bad = 0;
-            build_grid_warp(S.ge, P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, have_prev, lane, bad);  // :183-190
+            build_grid_warp(S.ge, spec[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, have_prev, lane, bad);  // :183-190
+            SQ_MARK(S, tid, 1);
             build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                                        // :191-199
             __syncwarp();
             patch_zero_angle(S.ge, P.e[0], lane);
+            SQ_MARK(S, tid, 7);
             if (bad) S.bad[0] = 1;
         }
         if (warp == (nwarps > 1 ? 1 : 0)) {
             int bad = 0;
-            build_grid_warp(S.go, P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, have_prev, lane, bad);     // :202-209
+            build_grid_warp(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, have_prev, lane, bad);  // :202-209
             __syncwarp();
             patch_zero_angle(S.go, P.e[1], lane);
             if (bad) S.bad[1] = 1;
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     const float invV = V > 0 ? __fdiv_rn(1.f, (float)V) : 0.f;
 
     for (int it = 0; it < A.n_iters; it++) {
-        sample_surface(S, tid, T, it > 0);
+        sample_surface(S, reinterpret_cast<GridSpec *>(smem_raw + sizeof(Smem)), tid, T, it > 0);
         const bool last = it == A.n_iters - 1;
 
         // ---- E ----
@@ -448,7 +459,7 @@ __global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int
     const int tid = threadIdx.x, obj = blockIdx.x;
     if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
     __syncthreads();
-    sample_surface(S, tid, blockDim.x, false);
+    sample_surface(S, reinterpret_cast<GridSpec *>(smem_raw + sizeof(Smem)), tid, blockDim.x, false);
     for (int i = tid; i < kN; i += blockDim.x) {
         float *o = out_xyz + ((size_t)obj * kN + i) * 3;
         o[0] = S.px[i]; o[1] = S.py[i]; o[2] = S.pz[i];
@@ -466,11 +477,15 @@ __global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const flo
     const float a1 = a[obj * 3 + 0], a2 = a[obj * 3 + 1], a3 = a[obj * 3 + 2];
     const float e1 = e[obj * 2 + 0], e2 = e[obj * 2 + 1];
     int bad = 0;
+    GridSpec *spec = reinterpret_cast<GridSpec *>(smem_raw + sizeof(Smem));
+    spec_powers(S.ge, spec[0], e1, pi_2, -pi_2, g_logtab[0], pi_2, false, tid, blockDim.x);
+    spec_powers(S.go, spec[1], e2, pi, -pi, g_logtab[1], pi_2, false, blockDim.x - 1 - tid, blockDim.x);
+    __syncthreads();
     if (warp == 0) {
-        build_grid_warp(S.ge, a1, a3, e1, pi_2, -pi_2, g_logtab[0], pi_2, false, lane, bad);
+        build_grid_warp(S.ge, spec[0], a1, a3, e1, pi_2, -pi_2, g_logtab[0], pi_2, false, lane, bad);
         build_cdf_warp(S.ge, S.cdf, __fadd_rn(a1, a2), lane);
     } else {
-        build_grid_warp(S.go, a1, a2, e2, pi, -pi, g_logtab[1], pi_2, false, lane, bad);
+        build_grid_warp(S.go, spec[1], a1, a2, e2, pi, -pi, g_logtab[1], pi_2, false, lane, bad);
     }
     __syncthreads();
     for (int i = tid; i < kN; i += blockDim.x) {
@@ -489,7 +504,7 @@ __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, cons
     const int tid = threadIdx.x, obj = blockIdx.x;
     if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
     __syncthreads();
-    sample_surface(S, tid, blockDim.x, false);
+    sample_surface(S, reinterpret_cast<GridSpec *>(smem_raw + sizeof(Smem)), tid, blockDim.x, false);
     const int v_begin = view_off[obj], V = view_off[obj + 1] - v_begin;
     for (int v = tid; v < V; v += blockDim.x) {
         float M[12];
@@ -627,9 +642,9 @@ static int ensure_init(int device)
     CU(cudaFuncSetAttribute(sq_optimize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
     CU(cudaFuncSetAttribute(sq_optimize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
     CU(cudaFuncSetAttribute(sq_optimize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
-    CU(cudaFuncSetAttribute(sq_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    CU(cudaFuncSetAttribute(sq_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    CU(cudaFuncSetAttribute(sq_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    CU(cudaFuncSetAttribute(sq_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    CU(cudaFuncSetAttribute(sq_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    CU(cudaFuncSetAttribute(sq_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
     CU(cudaSetDevice(cur));
     D.ready = true;
@@ -655,7 +670,7 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     }
     if (threads % 32 || threads < 32 || threads > 1024) return ODAM_SQ_ERR_ARG;
     long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
-    long smem = (long)sizeof(Smem) + items * 4 * 8;
+    long smem = (long)sizeof(Smem) + std::max<long>(items * 4 * 8, (long)kSpecBytes);  // phase-E results alias the B0 scratch
     if (smem > smem_optin) return ODAM_SQ_ERR_CONFIG;
     L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem;
     return ODAM_SQ_OK;
@@ -825,7 +840,7 @@ int odam_sq_sample_points(const float *params, int n, float *out_xyz, void *stre
     CU(cudaGetDevice(&device));
     int rc = ensure_init(device);
     if (rc) return rc;
-    sq_points_kernel<<<n, 256, sizeof(Smem), (cudaStream_t)stream>>>(params, n, out_xyz);
+    sq_points_kernel<<<n, 256, kFwdSmem, (cudaStream_t)stream>>>(params, n, out_xyz);
     CU(cudaGetLastError());
     return ODAM_SQ_OK;
 }
@@ -839,7 +854,7 @@ int odam_sq_project_boxes(const float *params, const int32_t *view_off, const fl
     CU(cudaGetDevice(&device));
     int rc = ensure_init(device);
     if (rc) return rc;
-    sq_boxes_kernel<<<n, 256, sizeof(Smem), (cudaStream_t)stream>>>(params, view_off, Ms, n, out_box);
+    sq_boxes_kernel<<<n, 256, kFwdSmem, (cudaStream_t)stream>>>(params, view_off, Ms, n, out_box);
     CU(cudaGetLastError());
     return ODAM_SQ_OK;
 }
@@ -974,7 +989,7 @@ int odam_sq_sample_points_host(const float *params, int n, float *out_xyz, int d
     unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
     memcpy(h, params, sizeof(float) * 9 * n);
     CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
-    sq_points_kernel<<<n, 256, sizeof(Smem), D.stream>>>((float *)d, n, (float *)(d + in_b));
+    sq_points_kernel<<<n, 256, kFwdSmem, D.stream>>>((float *)d, n, (float *)(d + in_b));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h + in_b, d + in_b, out_b, cudaMemcpyDeviceToHost, D.stream));
     CU(cudaStreamSynchronize(D.stream));
@@ -1006,7 +1021,7 @@ int odam_sq_project_boxes_host(const float *params, const int32_t *view_off, con
     memcpy(h + o_v, view_off, sizeof(int32_t) * (n + 1));
     memcpy(h + o_M, Ms, sizeof(float) * 12 * SV);
     CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
-    sq_boxes_kernel<<<n, 256, sizeof(Smem), D.stream>>>((float *)(d + o_p), (int32_t *)(d + o_v), (float *)(d + o_M), n,
+    sq_boxes_kernel<<<n, 256, kFwdSmem, D.stream>>>((float *)(d + o_p), (int32_t *)(d + o_v), (float *)(d + o_M), n,
                                                          (float *)(d + in_b));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h + in_b, d + in_b, out_b, cudaMemcpyDeviceToHost, D.stream));
@@ -1040,7 +1055,7 @@ int odam_sq_sample_on_batch_host(const float *shapes, const float *epsilons, flo
     memcpy(h + o_a, shapes, sizeof(float) * 3 * n);
     memcpy(h + o_e, epsilons, sizeof(float) * 2 * n);
     CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
-    sq_angles_kernel<<<n, 64, sizeof(Smem), D.stream>>>((float *)(d + o_a), (float *)(d + o_e), n, (float *)(d + o_eta),
+    sq_angles_kernel<<<n, 64, kFwdSmem, D.stream>>>((float *)(d + o_a), (float *)(d + o_e), n, (float *)(d + o_eta),
                                                          (float *)(d + o_om));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h + in_b, d + in_b, C.off - in_b, cudaMemcpyDeviceToHost, D.stream));

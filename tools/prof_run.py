@@ -45,8 +45,8 @@ if a.cycles:
     api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc)
     torch.cuda.synchronize()
     c = cyc.cpu().numpy().astype(float) / iters
-    names = ["A derive", "B/C grids+cdf", "D points", "E project", "F backward", "G reduce+loss", "Adam", "-"]
+    names = ["A derive", "B spec+eta walk (+wait omega)", "D points", "E project", "F backward", "G reduce+loss", "Adam", "C cdf+patch"]
     print("mean SM cycles per iteration per object (thread 0's view):")
-    for k in range(7):
-        print(f"  {names[k]:14s} {c[:, k].mean():9.0f}  ({c[:, k].mean() / c[:, :7].sum(1).mean():5.1%})")
-    print(f"  total          {c[:, :7].sum(1).mean():9.0f}")
+    for k in range(8):
+        print(f"  {names[k]:30s} {c[:, k].mean():9.0f}  ({c[:, k].mean() / c.sum(1).mean():5.1%})")
+    print(f"  total          {c.sum(1).mean():9.0f}")
