@@ -40,7 +40,7 @@ struct alignas(16) Smem {
     Pose pose;
     int status;
     int bad[2];
-    long long tmark, cyc[8];                // per-phase clock64() accumulation by thread 0 (diagnostics)
+    long long tmark, cyc[12];                // per-phase clock64() accumulation by thread 0 (diagnostics)
 };
 
 #define SQ_MARK(S, tid, k)                                                \
@@ -53,7 +53,7 @@ struct alignas(16) Smem {
     } while (0)
 
 constexpr size_t kSpecBytes = 2 * sizeof(GridSpec);
-constexpr size_t kFwdSmem = sizeof(Smem) + kSpecBytes;  // forward-only kernels: fixed part + B0 scratch
+constexpr size_t kFwdSmem = kSpecBytes;  // forward-only kernels: dynamic part = B0 scratch (Smem itself is static)
 
 struct OptArgs {
     const float *init; const int32_t *cls; const int32_t *view_off;
@@ -100,11 +100,13 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
         spec_powers(S.ge, spec[0], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, have_prev, tid, nthreads);
         spec_powers(S.go, spec[1], P.e[1], pi, -pi, g_logtab[1], pi_2, have_prev, nthreads - 1 - tid, nthreads);
         __syncthreads();
+        SQ_MARK(S, tid, 8);
         if (have_prev) {
             spec_ratios(S.ge, spec[0], P.a[0], P.a[2], true, tid, nthreads);
             spec_ratios(S.go, spec[1], P.a[0], P.a[1], true, nthreads - 1 - tid, nthreads);
             __syncthreads();
         }
+        SQ_MARK(S, tid, 9);
     }
     // ---- B, C ----
     {
@@ -128,7 +130,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
         }
     }
     __syncthreads();
-    SQ_MARK(S, tid, 1);
+    SQ_MARK(S, tid, 10);
     // ---- D ----
     {
         const Pose P = S.pose;
@@ -229,15 +231,16 @@ __device__ __forceinline__ int resolve_arg(const Smem &S, const float (&M)[12], 
 template <int kMaxThreads>
 __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_kernel(OptArgs A)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    // fixed state in static shared memory (compile-time addresses), per-launch scratch in dynamic shared memory
+    __shared__ Smem S;
+    extern __shared__ __align__(16) unsigned char scratch_raw[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
     const int obj = blockIdx.x;
     const int v_begin = A.view_off[obj];
     const int V = A.view_off[obj + 1] - v_begin;
     // per-item results live after the fixed part of shared memory
-    float *ext_val = reinterpret_cast<float *>(smem_raw + sizeof(Smem));
+    float *ext_val = reinterpret_cast<float *>(scratch_raw);
 
     int slices = V > 0 ? T / V : 1;
     slices = max(1, min(slices, A.max_slices));
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     if (tid < 3) S.s0[tid] = A.s0 ? A.s0[(size_t)obj * 3 + tid] : A.init[(size_t)obj * 9 + 4 + tid];
     if (tid == 0) {
         S.status = 0;
-        for (int k = 0; k < 8; k++) S.cyc[k] = 0;
+        for (int k = 0; k < 12; k++) S.cyc[k] = 0;
         S.tmark = clock64();
     }
     __syncthreads();
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     const float invV = V > 0 ? __fdiv_rn(1.f, (float)V) : 0.f;
 
     for (int it = 0; it < A.n_iters; it++) {
-        sample_surface(S, reinterpret_cast<GridSpec *>(smem_raw + sizeof(Smem)), tid, T, it > 0);
+        sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, T, it > 0);
         const bool last = it == A.n_iters - 1;
 
         // ---- E ----
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         __syncthreads();
         SQ_MARK(S, tid, 6);
     }
-    if (A.out_cycles && tid < 8) A.out_cycles[(size_t)obj * 8 + tid] = S.cyc[tid];
+    if (A.out_cycles && tid < 12) A.out_cycles[(size_t)obj * 12 + tid] = S.cyc[tid];
     if (tid < 9) {
         float p = S.par[tid];
         A.out_params[(size_t)obj * 9 + tid] = p;
@@ -454,12 +457,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
 // forward only: compute_ellipsoid_points for n objects, one CTA each
 __global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int n, float *out_xyz)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    __shared__ Smem S;
+    extern __shared__ __align__(16) unsigned char scratch_raw[];
     const int tid = threadIdx.x, obj = blockIdx.x;
     if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
     __syncthreads();
-    sample_surface(S, reinterpret_cast<GridSpec *>(smem_raw + sizeof(Smem)), tid, blockDim.x, false);
+    sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
     for (int i = tid; i < kN; i += blockDim.x) {
         float *o = out_xyz + ((size_t)obj * kN + i) * 3;
         o[0] = S.px[i]; o[1] = S.py[i]; o[2] = S.pz[i];
@@ -470,14 +473,14 @@ __global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int
 // buffer_size=201, seed=0): a[n][3], e[n][2] -> etas[n][1000], omegas[n][1000].  One CTA (2 warps) per primitive.
 __global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const float *e, int n, float *etas, float *omegas)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    __shared__ Smem S;
+    extern __shared__ __align__(16) unsigned char scratch_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, obj = blockIdx.x;
     const float pi = 3.14159274101257324f, pi_2 = __fmul_rn(pi, 0.5f);
     const float a1 = a[obj * 3 + 0], a2 = a[obj * 3 + 1], a3 = a[obj * 3 + 2];
     const float e1 = e[obj * 2 + 0], e2 = e[obj * 2 + 1];
     int bad = 0;
-    GridSpec *spec = reinterpret_cast<GridSpec *>(smem_raw + sizeof(Smem));
+    GridSpec *spec = reinterpret_cast<GridSpec *>(scratch_raw);
     spec_powers(S.ge, spec[0], e1, pi_2, -pi_2, g_logtab[0], pi_2, false, tid, blockDim.x);
     spec_powers(S.go, spec[1], e2, pi, -pi, g_logtab[1], pi_2, false, blockDim.x - 1 - tid, blockDim.x);
     __syncthreads();
@@ -499,12 +502,12 @@ __global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const flo
 __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, const int32_t *view_off,
                                                         const float *Ms, int n, float *out_box)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    __shared__ Smem S;
+    extern __shared__ __align__(16) unsigned char scratch_raw[];
     const int tid = threadIdx.x, obj = blockIdx.x;
     if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
     __syncthreads();
-    sample_surface(S, reinterpret_cast<GridSpec *>(smem_raw + sizeof(Smem)), tid, blockDim.x, false);
+    sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
     const int v_begin = view_off[obj], V = view_off[obj + 1] - v_begin;
     for (int v = tid; v < V; v += blockDim.x) {
         float M[12];
@@ -670,8 +673,8 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     }
     if (threads % 32 || threads < 32 || threads > 1024) return ODAM_SQ_ERR_ARG;
     long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
-    long smem = (long)sizeof(Smem) + std::max<long>(items * 4 * 8, (long)kSpecBytes);  // phase-E results alias the B0 scratch
-    if (smem > smem_optin) return ODAM_SQ_ERR_CONFIG;
+    long smem = std::max<long>(items * 4 * 8, (long)kSpecBytes);  // dynamic part: phase-E results alias the B0 scratch
+    if (smem + (long)sizeof(Smem) > smem_optin) return ODAM_SQ_ERR_CONFIG;
     L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem;
     return ODAM_SQ_OK;
 }
@@ -760,7 +763,8 @@ int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *
     if (rc) return rc;
     if (threads) *threads = L.threads;
     if (smem_bytes) *smem_bytes = L.smem;
-    if (ctas_per_sm) *ctas_per_sm = std::min({32, 2048 / L.threads, (233472 - 1024) / (L.smem + 1024)});
+    if (smem_bytes) *smem_bytes += (int)sizeof(Smem);
+    if (ctas_per_sm) *ctas_per_sm = std::min({32, 2048 / L.threads, 65536 / (64 * L.threads), (233472 - 1024) / (L.smem + (int)sizeof(Smem) + 1024)});
     return ODAM_SQ_OK;
 }
 

@@ -41,12 +41,13 @@ for k in range(a.launches):
           f"{api.algorithmic_flops(tracks.view_off[1:] - tracks.view_off[:-1], iters) / ms / 1e9:.2f} TFLOP/s")
 print("flagged", int((out["status"].cpu() & 3 != 0).sum()))
 if a.cycles:
-    cyc = torch.zeros((tracks.n, 8), dtype=torch.int64, device="cuda:0")
+    cyc = torch.zeros((tracks.n, 12), dtype=torch.int64, device="cuda:0")
     api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc)
     torch.cuda.synchronize()
     c = cyc.cpu().numpy().astype(float) / iters
-    names = ["A derive", "B spec+eta walk (+wait omega)", "D points", "E project", "F backward", "G reduce+loss", "Adam", "C cdf+patch"]
+    names = ["A derive", "B eta walk", "D points", "E project", "F backward", "G reduce+loss", "Adam", "C cdf+patch",
+             "B0 powers (+barrier)", "B0 ratios (+barrier)", "wait for omega warp", "-"]
     print("mean SM cycles per iteration per object (thread 0's view):")
-    for k in range(8):
+    for k in range(11):
         print(f"  {names[k]:30s} {c[:, k].mean():9.0f}  ({c[:, k].mean() / c.sum(1).mean():5.1%})")
     print(f"  total          {c.sum(1).mean():9.0f}")
