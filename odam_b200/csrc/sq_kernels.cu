@@ -642,9 +642,9 @@ static int ensure_init(int device)
         std::copy(one.begin(), one.end(), tab.begin() + kTabSize);
         CU(cudaMemcpyToSymbol(g_logtab, tab.data(), sizeof(double2) * 2 * kTabSize));
     }
-    CU(cudaFuncSetAttribute(sq_optimize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
-    CU(cudaFuncSetAttribute(sq_optimize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
-    CU(cudaFuncSetAttribute(sq_optimize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin));
+    CU(cudaFuncSetAttribute(sq_optimize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
+    CU(cudaFuncSetAttribute(sq_optimize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
+    CU(cudaFuncSetAttribute(sq_optimize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
     CU(cudaFuncSetAttribute(sq_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaFuncSetAttribute(sq_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaFuncSetAttribute(sq_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
