@@ -87,45 +87,46 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
             sq_sincos_pi(S.par[3], sd, cd);  // yaw: correctly rounded cos/sin for |angle| < ~1e5 rad
             P.cz = (float)cd; P.sz = (float)sd;
             S.bad[0] = 0; S.bad[1] = 0;
+            S.ge.fix_lo = S.ge.count; S.go.fix_lo = S.go.count;
         }
     }
     __syncthreads();
     SQ_MARK(S, tid, 0);
-    // ---- B0: everything about the previous tree's nodes that does not depend on slot counts (all threads) ----
+    // ---- B0: node pool of the previous tree -> powers, split ratios, slots (all threads) ----
     const float pi = 3.14159274101257324f;       // (float)acos(-1), sampling.cpp:14
     const float pi_2 = __fmul_rn(pi, 0.5f);      // pi/2, :15
     {
         const Pose &P = S.pose;
         // the two grids are interleaved from opposite ends so that every warp gets a share of both
-        spec_powers(S.ge, spec[0], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, have_prev, tid, nthreads);
-        spec_powers(S.go, spec[1], P.e[1], pi, -pi, g_logtab[1], pi_2, have_prev, nthreads - 1 - tid, nthreads);
+        pool_powers(S.ge, spec[0], P.e[0], g_logtab[0], pi_2, tid, nthreads);
+        pool_powers(S.go, spec[1], P.e[1], g_logtab[1], pi_2, nthreads - 1 - tid, nthreads);
         __syncthreads();
         SQ_MARK(S, tid, 8);
-        if (have_prev) {
-            spec_ratios(S.ge, spec[0], P.a[0], P.a[2], true, tid, nthreads);
-            spec_ratios(S.go, spec[1], P.a[0], P.a[1], true, nthreads - 1 - tid, nthreads);
-            __syncthreads();
-        }
+        pool_ratios(S.ge, spec[0], P.a[0], P.a[2], tid, nthreads);
+        pool_ratios(S.go, spec[1], P.a[0], P.a[1], nthreads - 1 - tid, nthreads);
+        __syncthreads();
+        int bad0 = 0, bad1 = 0;
+        pool_place(S.ge, spec[0], tid, nthreads, bad0);
+        pool_place(S.go, spec[1], nthreads - 1 - tid, nthreads, bad1);
+        if (bad0) S.bad[0] = 1;
+        if (bad1) S.bad[1] = 1;
+        __syncthreads();
         SQ_MARK(S, tid, 9);
     }
-    // ---- B, C ----
+    // ---- B, C: fix-up walk over new nodes (everything on the first iteration), then the CDF ----
     {
         const Pose &P = S.pose;
         if (warp == 0) {
             int bad = 0;
-            build_grid_warp(S.ge, spec[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, have_prev, lane, bad);  // :183-190
+            pool_walk(S.ge, spec[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);  // :183-190
             SQ_MARK(S, tid, 1);
-            build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                                        // :191-199
-            __syncwarp();
-            patch_zero_angle(S.ge, P.e[0], lane);
-            SQ_MARK(S, tid, 7);
+            build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                                // :191-199
             if (bad) S.bad[0] = 1;
+            SQ_MARK(S, tid, 7);
         }
         if (warp == (nwarps > 1 ? 1 : 0)) {
             int bad = 0;
-            build_grid_warp(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, have_prev, lane, bad);  // :202-209
-            __syncwarp();
-            patch_zero_angle(S.go, P.e[1], lane);
+            pool_walk(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad);     // :202-209
             if (bad) S.bad[1] = 1;
         }
     }
@@ -155,7 +156,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
                 if (!ok) j = lower_bound_201(S.cdf, uu);
                 int k = g_k_omega[i];
                 float x0, y0, z0, X, Y, Z;
-                local_point(P, S.ge, S.go, j, k, x0, y0, z0);
+                local_point(P, S.ge.slot[j], S.go.slot[k], x0, y0, z0);
                 to_world(P, clamp_eps(x0), clamp_eps(y0), clamp_eps(z0), X, Y, Z);
                 S.px[i] = X; S.py[i] = Y; S.pz[i] = Z; S.pj[i] = (uint8_t)j;
             } else {  // padding: never valid (NaN is ignored by min/max)
@@ -258,6 +259,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         S.status = 0;
         for (int k = 0; k < 12; k++) S.cyc[k] = 0;
         S.tmark = clock64();
+        const float pi = 3.14159274101257324f, pi_2 = __fmul_rn(pi, 0.5f);
+        pool_init(S.ge, pi_2, -pi_2);
+        pool_init(S.go, pi, -pi);
     }
     __syncthreads();
 
@@ -339,15 +343,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             float gp1 = __fmaf_rn(M[9], g_z, __fmul_rn(sd < 2 ? M[1] : M[5], g_lin));
             float gp2 = __fmaf_rn(M[10], g_z, __fmul_rn(sd < 2 ? M[2] : M[6], g_lin));
             int j = S.pj[arg], k = g_k_omega[arg];
+            const float4 se = S.ge.slot[j], so = S.go.slot[k];
             float x0, y0, z0;
-            local_point(P, S.ge, S.go, j, k, x0, y0, z0);
+            local_point(P, se, so, x0, y0, z0);
             float x = clamp_eps(x0), y = clamp_eps(y0);
             acc[0] += gp0; acc[1] += gp1; acc[2] += gp2;
             acc[3] += gp0 * (-x * P.sz - y * P.cz) + gp1 * (x * P.cz - y * P.sz);
             float gl0 = (P.cz * gp0 + P.sz * gp1) * clamp_grad(x0);
             float gl1 = (-P.sz * gp0 + P.cz * gp1) * clamp_grad(y0);
             float gl2 = gp2 * clamp_grad(z0);
-            float fce = S.ge.fc[j], fse = S.ge.fs[j], fco = S.go.fc[k], fso = S.go.fs[k];
+            float fce = se.y, fse = se.z, fco = so.y, fso = so.z;
             acc[4] += 2.f * S.par[4] * (gl0 * fce * fco);
             acc[5] += 2.f * S.par[5] * (gl1 * fce * fso);
             acc[6] += 2.f * S.par[6] * (gl2 * fse);
@@ -434,8 +439,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         if (last) {
             if (A.out_eta_idx) for (int i = tid; i < kN; i += T) A.out_eta_idx[(size_t)obj * kN + i] = S.pj[i];
             if (A.out_grids) for (int i = tid; i < kG; i += T) {
-                A.out_grids[((size_t)obj * 2 + 0) * kG + i] = S.ge.th[i];
-                A.out_grids[((size_t)obj * 2 + 1) * kG + i] = S.go.th[i];
+                A.out_grids[((size_t)obj * 2 + 0) * kG + i] = S.ge.slot[i].x;
+                A.out_grids[((size_t)obj * 2 + 1) * kG + i] = S.go.slot[i].x;
             }
         }
         __syncthreads();
@@ -461,6 +466,11 @@ __global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int
     extern __shared__ __align__(16) unsigned char scratch_raw[];
     const int tid = threadIdx.x, obj = blockIdx.x;
     if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
+    if (tid == 0) {
+        const float pi = 3.14159274101257324f, pi_2 = __fmul_rn(pi, 0.5f);
+        pool_init(S.ge, pi_2, -pi_2);
+        pool_init(S.go, pi, -pi);
+    }
     __syncthreads();
     sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
     for (int i = tid; i < kN; i += blockDim.x) {
@@ -481,19 +491,21 @@ __global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const flo
     const float e1 = e[obj * 2 + 0], e2 = e[obj * 2 + 1];
     int bad = 0;
     GridSpec *spec = reinterpret_cast<GridSpec *>(scratch_raw);
-    spec_powers(S.ge, spec[0], e1, pi_2, -pi_2, g_logtab[0], pi_2, false, tid, blockDim.x);
-    spec_powers(S.go, spec[1], e2, pi, -pi, g_logtab[1], pi_2, false, blockDim.x - 1 - tid, blockDim.x);
+    if (tid == 0) { pool_init(S.ge, pi_2, -pi_2); pool_init(S.go, pi, -pi); }
+    __syncthreads();
+    pool_powers(S.ge, spec[0], e1, g_logtab[0], pi_2, tid, blockDim.x);      // end points only (empty pool)
+    pool_powers(S.go, spec[1], e2, g_logtab[1], pi_2, blockDim.x - 1 - tid, blockDim.x);
     __syncthreads();
     if (warp == 0) {
-        build_grid_warp(S.ge, spec[0], a1, a3, e1, pi_2, -pi_2, g_logtab[0], pi_2, false, lane, bad);
+        pool_walk(S.ge, spec[0], a1, a3, e1, pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);
         build_cdf_warp(S.ge, S.cdf, __fadd_rn(a1, a2), lane);
     } else {
-        build_grid_warp(S.go, spec[1], a1, a2, e2, pi, -pi, g_logtab[1], pi_2, false, lane, bad);
+        pool_walk(S.go, spec[1], a1, a2, e2, pi, -pi, g_logtab[1], pi_2, lane, bad);
     }
     __syncthreads();
     for (int i = tid; i < kN; i += blockDim.x) {
-        etas[(size_t)obj * kN + i] = S.ge.th[lower_bound_201(S.cdf, g_u_eta[i])];
-        omegas[(size_t)obj * kN + i] = S.go.th[g_k_omega[i]];
+        etas[(size_t)obj * kN + i] = S.ge.slot[lower_bound_201(S.cdf, g_u_eta[i])].x;
+        omegas[(size_t)obj * kN + i] = S.go.slot[g_k_omega[i]].x;
     }
 }
 
@@ -506,6 +518,11 @@ __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, cons
     extern __shared__ __align__(16) unsigned char scratch_raw[];
     const int tid = threadIdx.x, obj = blockIdx.x;
     if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
+    if (tid == 0) {
+        const float pi = 3.14159274101257324f, pi_2 = __fmul_rn(pi, 0.5f);
+        pool_init(S.ge, pi_2, -pi_2);
+        pool_init(S.go, pi, -pi);
+    }
     __syncthreads();
     sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
     const int v_begin = view_off[obj], V = view_off[obj + 1] - v_begin;
