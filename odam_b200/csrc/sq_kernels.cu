@@ -88,6 +88,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
             P.cz = (float)cd; P.sz = (float)sd;
             S.bad[0] = 0; S.bad[1] = 0;
             S.ge.fix_lo = S.ge.count; S.go.fix_lo = S.go.count;
+            S.ge.changed = 0; S.go.changed = 0;
         }
     }
     __syncthreads();
