@@ -168,6 +168,52 @@ def main():
         print(f"case {k}: obj {i} {rep} prior={pr} iters={iters} V={V}: loss {rec['loss'][0]:.4f} -> "
               f"{rec['loss'][-1]:.4f}; torch_oracle bit-identical")
     np.savez_compressed(os.path.join(OUT, "ref_runs.npz"), **out)
+
+    # ---- 3c. call-site helpers (staging before, oriented box after the optimiser) ----
+    import types
+    for name in ("quaternion", "easydict", "open3d", "matplotlib", "matplotlib.pyplot", "matplotlib.patches",
+                 "matplotlib._color_data", "plyfile", "trimesh"):
+        sys.modules.setdefault(name, types.ModuleType(name))   # test-only shims for imports the path never calls
+    sys.modules["easydict"].EasyDict = dict
+    sys.modules["plyfile"].PlyData = sys.modules["plyfile"].PlyElement = None
+    import src.utils.box_utils as box_utils
+    import src.utils.tracking_gt_utils as tgu
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(77)
+    n_frames = 30
+    frame_ids = np.arange(100, 100 + n_frames)
+    T_wcs = [np.eye(4) for _ in range(n_frames)]
+    K = synthetic.K
+    cs = dict(frame_ids=frame_ids)
+    for t in range(4):
+        nrow = int(rng.integers(5, 25))
+        frames = np.sort(rng.choice(frame_ids, nrow, replace=False))
+        track = -np.ones((nrow, 82))
+        track[:, 0] = frames
+        track[:, 1] = rng.integers(0, 8, nrow)
+        x0, y0 = rng.uniform(-30, 900, nrow), rng.uniform(-30, 600, nrow)
+        track[:, 2:6] = np.stack([x0, y0, x0 + rng.uniform(40, 500, nrow), y0 + rng.uniform(40, 420, nrow)], 1)
+        track[:, 6:9] = rng.uniform(0.3, 1.5, (nrow, 3))
+        track[:, 9:12] = rng.normal(0, 1, 3)[None] + rng.normal(0, 0.05, (nrow, 3))
+        track[:, 12] = rng.uniform(-0.3, 0.3) + rng.normal(0, 0.1, nrow)
+        track[:, 13] = rng.uniform(0.5, 1, nrow)
+        lines, bl, pv, oc, T_wos, scales, dp = tgu.load_pred_object(track, frame_ids, T_wcs, 968, 1296, K)
+        T_wo = tgu.averaging_T_wos(T_wos)
+        sc = np.mean(np.asarray([x for x in scales if len(x) > 0]), axis=0)
+        valid = [i for i in range(n_frames) if len(bl[i]) > 0]
+        boxv = np.zeros((len(valid), 4)); maskv = np.zeros((len(valid), 4), np.uint8)
+        for a, i in enumerate(valid):
+            for b, nm in enumerate(("x_min", "x_max", "y_min", "y_max")):
+                if nm in bl[i]:
+                    boxv[a, b] = -bl[i][nm][-1]; maskv[a, b] = 1
+        cs.update({f"t{t}_track": track, f"t{t}_class": oc, f"t{t}_T_wo": T_wo, f"t{t}_dims": sc,
+                   f"t{t}_valid": np.array(valid), f"t{t}_box": boxv, f"t{t}_mask": maskv,
+                   f"t{t}_yaw": Rotation.from_matrix(T_wo[:3, :3]).as_euler("zxy")[0],
+                   f"t{t}_bbox_dl": box_utils.get_3d_box(sc, T_wo[:3, :3], T_wo[:3, 3])})
+    for k in range(6):
+        cs[f"obb{k}_pts"] = out[f"c{k}_final_points"]
+        cs[f"obb{k}_box"] = box_utils.compute_oriented_bbox(out[f"c{k}_final_points"].astype(np.float64))
+    np.savez_compressed(os.path.join(OUT, "call_site.npz"), **cs)
     print("wrote", OUT)
 
 

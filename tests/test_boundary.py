@@ -1,0 +1,140 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol include/odam_sq.h declares,
+the product package never touches oracle/, and the host-side mirror of the reference interface behaves."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from odam_b200 import build
+    build.build()
+    from odam_b200 import _lib
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(REPO, "include", "odam_sq.h")).read()
+    declared = set(re.findall(r"\b(odam_sq_[a-z_0-9]+)\s*\(", hdr))
+    assert {"odam_sq_optimize", "odam_sq_optimize_host", "odam_sq_sample_points_host",
+            "odam_sq_sample_on_batch_host", "odam_sq_project_boxes_host"} <= declared
+    for name in declared:
+        assert hasattr(lib, name), name
+    from odam_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+    assert lib.odam_sq_abi_version() == 1
+    assert lib.odam_sq_error_string(-1) == b"invalid argument"
+
+
+def test_options_struct_layout_matches_header():
+    """ctypes mirror of odam_sq_options: field order/names as in the header."""
+    from odam_b200 import _lib
+    hdr = open(os.path.join(REPO, "include", "odam_sq.h")).read()
+    body = hdr[hdr.index("typedef struct odam_sq_options {"):hdr.index("} odam_sq_options;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\b\*?\s*([a-z_0-9]+)\s*;", body)
+    assert names == [f[0] for f in _lib.Options._fields_]
+
+
+def test_argument_validation_without_gpu(lib):
+    """Bad arguments are rejected before any CUDA call (so this runs on a CPU-only box)."""
+    z = ctypes.c_void_p(0)
+    assert lib.odam_sq_optimize_host(z, z, z, z, z, z, z, 1, 1, 0, 0.01, 0.1, z, z, z, None, 0) == -1
+    assert lib.odam_sq_sample_on_batch_host(z, z, z, z, 1, 1, 1000, 201, 0, 0) == -1
+    a = np.zeros(3, np.float32)
+    p = a.ctypes.data_as(ctypes.c_void_p)
+    assert lib.odam_sq_sample_on_batch_host(p, p, p, p, 1, 1, 999, 201, 0, 0) == -1   # only N=1000 / 201 / seed 0
+    th, sm, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    voff = np.array([0, 20, 40], np.int32)
+    assert lib.odam_sq_query_launch(voff.ctypes.data_as(ctypes.c_void_p), 2, None, ctypes.byref(th), ctypes.byref(sm),
+                                    ctypes.byref(c)) == 0
+    assert th.value % 32 == 0 and 32 <= th.value <= 1024 and sm.value > 0 and c.value >= 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    from odam_b200 import _lib, api, synthetic
+    tracks = api.pack_scene(synthetic.make_scene(2, 10, seed=3))
+    with pytest.raises(_lib.OdamSqError):
+        api.optimize_host(tracks, n_iters=1)
+
+
+def test_product_never_imports_oracle():
+    """Static: no file under odam_b200/ mentions the oracle package; dynamic: importing the product does not load it."""
+    for root, _, files in os.walk(os.path.join(REPO, "odam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+(\.+)?oracle\b", txt, re.M), f
+                assert not re.search(r"sq_oracle|c_oracle|torch_oracle|libsq_oracle", txt), f
+    code = ("import sys; sys.path.insert(0, %r); import odam_b200.sq_libs, odam_b200.run_multi_view, odam_b200.api; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)" % REPO)
+    subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_packing_mirrors_reference_line_dicts():
+    from odam_b200 import api, synthetic
+    scene = synthetic.make_scene(3, 12, seed=2)
+    tr = api.pack_scene(scene)
+    for i in range(3):
+        box, mask = api.pack_lines(scene.gt_lines(i))
+        a, b = tr.view_off[i], tr.view_off[i + 1]
+        assert np.array_equal(mask, tr.mask[a:b]) and np.array_equal(box[mask > 0], tr.box[a:b][mask > 0])
+    p = api.init_params([1, 2, 3], 0.5, [0.5, 0.72, 0.98], "cube")
+    assert np.allclose(p[4:7], np.sqrt(np.array([0.5, 0.72, 0.98]) / 2)) and np.all(p[7:9] == -10000)
+    assert np.signbit(api.init_params([0, 0, 0], 0, [1, 1, 1])[7])  # shapes start at -0.0 (sq_libs.py:369)
+    sub = tr.slice(1, 3)
+    assert sub.n == 2 and sub.view_off[0] == 0 and sub.total_views == tr.view_off[3] - tr.view_off[1]
+
+
+def test_prior_table_matches_reference_data(golden_runs):
+    from odam_b200 import api
+    tab = api.prior_table()
+    assert tab.shape == (8, 9)
+    assert np.array_equal(tab, golden_runs["prior_by_class"].astype(np.float32).reshape(8, 9))
+
+
+def test_optimizer_constructor_mirrors_reference():
+    from odam_b200.sq_libs import SuperQuadricOptimizer
+    o = SuperQuadricOptimizer(np.array([0.1, 0.2, 0.3]), 0.4, np.array([0.5, 0.6, 0.7]), 5, "super_quadric", True)
+    q = o.Q_init
+    assert q.obj_class == 5 and o.use_prior and o.loss_log == []
+    assert q.scales.dtype.is_floating_point and q.scales.requires_grad and q.translate.requires_grad
+    assert np.allclose(q.scales.detach().numpy(), np.sqrt(np.array([0.5, 0.6, 0.7]) / 2).astype(np.float32))
+    assert set(o.scale_prior) == {"03211117", "04379243", "02808440", "02747177", "04256520", "03001627", "02933112",
+                                  "02871439"}
+    with pytest.raises(AssertionError):
+        SuperQuadricOptimizer(np.zeros(3), 0.0, np.ones(3), 0, "sphere", True)
+    import pickle
+    q2 = pickle.loads(pickle.dumps(q))   # results are pickled per sequence (run_processor.py:85-92)
+    assert np.array_equal(q2.params(), q.params())
+
+
+def test_call_site_staging_matches_reference():
+    """stage_object / get_3d_box / compute_oriented_bbox against outputs of the reference's own helpers."""
+    from odam_b200 import api
+    from odam_b200.postprocess import compute_oriented_bbox, get_3d_box
+    from odam_b200.run_multi_view import stage_object
+    from scipy.spatial.transform import Rotation
+    G = np.load(os.path.join(REPO, "tests", "golden", "call_site.npz"))
+    for t in range(4):
+        s = stage_object(G[f"t{t}_track"], G["frame_ids"], 968, 1296)
+        assert s["obj_class"] == int(G[f"t{t}_class"])
+        assert np.allclose(s["t_wo"], G[f"t{t}_T_wo"][:3, 3]) and np.allclose(s["R"], G[f"t{t}_T_wo"][:3, :3])
+        assert np.allclose(s["dims"], G[f"t{t}_dims"])
+        assert np.array_equal(np.array(s["valid_frames"]), G[f"t{t}_valid"])
+        box, mask = api.pack_lines(s["lines"])
+        assert np.array_equal(mask, G[f"t{t}_mask"]) and np.allclose(box, G[f"t{t}_box"].astype(np.float32))
+        assert np.isclose(Rotation.from_matrix(s["R"]).as_euler("zxy")[0], float(G[f"t{t}_yaw"]))
+        assert np.allclose(get_3d_box(s["dims"], s["R"], s["t_wo"]), G[f"t{t}_bbox_dl"])
+    for k in range(6):
+        assert np.allclose(compute_oriented_bbox(G[f"obb{k}_pts"]), G[f"obb{k}_box"], atol=1e-9)
