@@ -71,7 +71,7 @@ extern "C" {
 /* Optional knobs and test-only inputs/outputs; zero-initialise, then set what you need. */
 typedef struct odam_sq_options {
     int threads;            /* CTA size (multiple of 32, 32..1024); 0 = choose from the view counts   */
-    int max_slices;         /* max point-slices per view (1..8); 0 = default                           */
+    int max_slices;         /* max point-slices per view (1..25); 0 = default                          */
     int max_views;          /* device-pointer entry only: max views of any object, if the caller knows it
                                (with threads != 0 this avoids reading view_off back to the host)         */
     /* teacher forcing (tests): start from a recorded optimiser state instead of a fresh one          */

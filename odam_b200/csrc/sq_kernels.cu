@@ -678,12 +678,12 @@ struct LaunchCfg { int threads, max_slices, smem; };
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
                          int smem_optin, LaunchCfg &L)
 {
-    int max_slices = opt && opt->max_slices ? opt->max_slices : 8;
-    if (max_slices < 1 || max_slices > 8) return ODAM_SQ_ERR_ARG;
+    int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= 2 * sm_count ? 8 : 16);
+    if (max_slices < 1 || max_slices > 25) return ODAM_SQ_ERR_ARG;
     int threads = opt ? opt->threads : 0;
     if (threads == 0) {
         // throughput regime (many objects per SM): ~160 threads; latency regime (fewer CTAs than SMs): wider
-        int target = n >= 2 * sm_count ? 160 : 512;
+        int target = n >= 2 * sm_count ? 128 : 512;
         int v = std::max(1, (int)(mean_views + 0.5));
         int s = std::max(1, std::min(max_slices, target / v));
         threads = ((v * s + 31) / 32) * 32;
