@@ -182,6 +182,7 @@ __device__ __forceinline__ void load_M(const float *Ms, int gv, float (&M)[12])
 // phase E for one (view, slice) item: extrema over chunks [c0, c1) and, per side, the chunk that produced it
 // (-1 = no valid point improved on the +-1e6 sentinel).  The arg index is resolved later, only for the slice that
 // wins the cross-slice combine.
+template <bool kCheck>
 __device__ __forceinline__ void scan_item(const Smem &S, const float (&M)[12], int c0, int c1,
                                           float (&best)[4], int (&cid)[4])
 {
@@ -195,10 +196,10 @@ __device__ __forceinline__ void scan_item(const Smem &S, const float (&M)[12], i
 #pragma unroll
         for (int h = 0; h < kChunk / 4; h++) {
             float4 x = xs[h], y = ys[h], z = zs[h];
-            project_uv(M, x.x, y.x, z.x, u[4 * h + 0], w[4 * h + 0]);
-            project_uv(M, x.y, y.y, z.y, u[4 * h + 1], w[4 * h + 1]);
-            project_uv(M, x.z, y.z, z.z, u[4 * h + 2], w[4 * h + 2]);
-            project_uv(M, x.w, y.w, z.w, u[4 * h + 3], w[4 * h + 3]);
+            project_uv<kCheck>(M, x.x, y.x, z.x, u[4 * h + 0], w[4 * h + 0]);
+            project_uv<kCheck>(M, x.y, y.y, z.y, u[4 * h + 1], w[4 * h + 1]);
+            project_uv<kCheck>(M, x.z, y.z, z.z, u[4 * h + 2], w[4 * h + 2]);
+            project_uv<kCheck>(M, x.w, y.w, z.w, u[4 * h + 3], w[4 * h + 3]);
         }
         float n0 = best[0], n1 = best[1], n2 = best[2], n3 = best[3];
 #pragma unroll
@@ -221,10 +222,9 @@ __device__ __forceinline__ int resolve_arg(const Smem &S, const float (&M)[12], 
 {
     int found = -1;
     const int base = c * kChunk;
-#pragma unroll
     for (int h = kChunk - 1; h >= 0; h--) {
         float u, w;
-        project_uv(M, S.px[base + h], S.py[base + h], S.pz[base + h], u, w);
+        project_uv<true>(M, S.px[base + h], S.py[base + h], S.pz[base + h], u, w);
         if ((y_side ? w : u) == best) found = base + h;
     }
     return found;
@@ -277,10 +277,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             int sl = item / V, v = item - sl * V;
             float M[12];
             load_M(A.Ms, v_begin + v, M);
+            M[11] = __fadd_rn(M[11], 1e-6f);  // the reference's |z| + 1e-6, folded (see project_uv)
             int c0 = (sl * kNChunks) / slices, c1 = ((sl + 1) * kNChunks) / slices;
             float best[4];
             int cid[4];
-            scan_item(S, M, c0, c1, best, cid);
+            if (view_all_valid(M, S.pose)) scan_item<false>(S, M, c0, c1, best, cid);
+            else scan_item<true>(S, M, c0, c1, best, cid);
             reinterpret_cast<float4 *>(ext_val)[item] = make_float4(best[0], best[1], best[2], best[3]);
             reinterpret_cast<int4 *>(ext_arg)[item] = make_int4(cid[0], cid[1], cid[2], cid[3]);
         }
@@ -315,7 +317,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             int arg = -1;
             if (cid >= 0) {
                 load_M(A.Ms, gv, M);
+                const float m11 = M[11];
+                M[11] = __fadd_rn(m11, 1e-6f);
                 arg = resolve_arg(S, M, cid, sd >= 2, best);
+                M[11] = m11;
             }
             if (arg >= 0) {
                 float X = S.px[arg], Y = S.py[arg], Z = S.pz[arg];
