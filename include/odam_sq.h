@@ -72,6 +72,8 @@ extern "C" {
 typedef struct odam_sq_options {
     int threads;            /* CTA size (multiple of 32, 32..1024); 0 = choose from the view counts   */
     int max_slices;         /* max point-slices per view (1..25); 0 = default                          */
+    int cluster;            /* CTAs per object (thread-block cluster, views tiled across them): 1, 2 or 4; 0 = auto
+                               (2 or 4 when there are fewer objects than SMs)                                 */
     int max_views;          /* device-pointer entry only: max views of any object, if the caller knows it
                                (with threads != 0 this avoids reading view_off back to the host)         */
     /* teacher forcing (tests): start from a recorded optimiser state instead of a fresh one          */
@@ -139,7 +141,7 @@ int odam_sq_fma_peak(int device, double *tflops);
 
 /* The launch configuration odam_sq_optimize would use (for benchmarks/logging). */
 int odam_sq_query_launch(const int32_t *view_off_host, int n, const odam_sq_options *opt,
-                         int *threads, int *smem_bytes, int *ctas_per_sm);
+                         int *threads, int *smem_bytes, int *ctas_per_sm, int *cluster);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@
 //   G  deterministic CTA reduction of 9 gradients + 4 side sums, prior, Adam              [sq_libs.py:463-472]
 //
 // No tensor cores: the path is FP32 FMA + min/max + one MUFU.RCP per point-view.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -25,9 +26,12 @@
 #include "../../include/odam_sq.h"
 #include "sq_device.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace odam {
 
 constexpr int kMaxWarps = 32;
+constexpr int kMaxCluster = 4;   // CTAs per object (view-tiled thread-block cluster)
 constexpr int kRed = 13;  // 9 gradients + 4 side sums
 
 struct alignas(16) Smem {
@@ -36,6 +40,7 @@ struct alignas(16) Smem {
     float cdf[kGPad];
     uint8_t pj[kNPad];                      // eta-grid index of each sample
     float red[kMaxWarps][kRed + 3];
+    float xred[2][kMaxCluster][kRed + 3];   // per-CTA partial sums exchanged through DSMEM, double-buffered by iteration parity
     float par[12], m[12], v[12], s0[4], grad[12], prior[12];
     Pose pose;
     int status;
@@ -58,7 +63,7 @@ constexpr size_t kFwdSmem = kSpecBytes;  // forward-only kernels: dynamic part =
 struct OptArgs {
     const float *init; const int32_t *cls; const int32_t *view_off;
     const float *Ms; const float *box; const uint8_t *mask; const float *prior;
-    int n, n_iters, optimize_shapes, max_slices;
+    int n, n_iters, optimize_shapes, max_slices, cluster;
     const float *adam_tab;  // [n_iters][4]: -lr/bc1, -lr_shape/bc1, sqrt(bc2), unused
     float beta1w, beta2, beta2w, eps;
     const float *m0, *v0, *s0;
@@ -238,9 +243,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     extern __shared__ __align__(16) unsigned char scratch_raw[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
-    const int obj = blockIdx.x;
-    const int v_begin = A.view_off[obj];
-    const int V = A.view_off[obj + 1] - v_begin;
+    // A cluster of C CTAs shares one object: every CTA runs the (cheap, deterministic) sampler redundantly and
+    // projects its own tile of the views; the 13 partial sums meet through distributed shared memory once per iteration.
+    const int C = A.cluster;
+    const int obj = blockIdx.x / C, crank = blockIdx.x - obj * C;
+    const int v_obj = A.view_off[obj];
+    const int Vall = A.view_off[obj + 1] - v_obj;
+    const int v_begin = v_obj + (Vall * crank) / C;
+    const int V = v_obj + (Vall * (crank + 1)) / C - v_begin;   // this CTA's views
     // per-item results live after the fixed part of shared memory
     float *ext_val = reinterpret_cast<float *>(scratch_raw);
 
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     }
     __syncthreads();
 
-    const float invV = V > 0 ? __fdiv_rn(1.f, (float)V) : 0.f;
+    const float invV = Vall > 0 ? __fdiv_rn(1.f, (float)Vall) : 0.f;
 
     for (int it = 0; it < A.n_iters; it++) {
         sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, T, it > 0);
@@ -395,12 +405,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             float x = 0.f;
             for (int wi = 0; wi < nred; wi++) x += S.red[wi][tid];
             S.red[0][tid] = x;
+            if (C > 1) {  // hand this CTA's partial to every CTA of the cluster (including itself)
+                cg::cluster_group cl = cg::this_cluster();
+                for (int r = 0; r < C; r++) *cl.map_shared_rank(&S.xred[it & 1][crank][tid], r) = x;
+            }
+        }
+        if (C > 1) {
+            cg::this_cluster().sync();
+            if (tid < kRed) {  // same rank order in every CTA -> identical sums -> identical Adam steps
+                float x = 0.f;
+                for (int r = 0; r < C; r++) x += S.xred[it & 1][r][tid];
+                S.red[0][tid] = x;
+            }
         }
         __syncthreads();
         if (tid == 0) {
             // loss = sum over sides of mean over ALL views (sq_libs.py:428-429) + prior (:463-466)
             float loss = 0.f;
-            for (int sd = 0; sd < 4; sd++) loss = __fadd_rn(loss, __fdiv_rn(S.red[0][9 + sd], (float)V));
+            for (int sd = 0; sd < 4; sd++) loss = __fadd_rn(loss, __fdiv_rn(S.red[0][9 + sd], (float)Vall));
             float g[9];
             for (int k = 0; k < 9; k++) g[k] = S.red[0][k];
             if (A.prior) {
@@ -419,7 +441,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
                 loss = __fadd_rn(loss, __fmul_rn(q3, 20.f));
             }
             if (!A.optimize_shapes) { g[7] = 0.f; g[8] = 0.f; }
-            A.out_loss[(size_t)obj * A.n_iters + it] = loss;
+            if (crank == 0) A.out_loss[(size_t)obj * A.n_iters + it] = loss;
             bool finite = isfinite(loss);
             for (int k = 0; k < 9; k++) { S.grad[k] = g[k]; finite = finite && isfinite(g[k]); }
             if (!finite) S.status |= ODAM_SQ_ST_NONFINITE;
@@ -438,11 +460,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), A.eps);
             p = __fadd_rn(p, __fdiv_rn(__fmul_rn(alpha, m), denom));
             S.m[tid] = m; S.v[tid] = v; S.par[tid] = p;
-            if (A.out_param_hist) A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = p;
+            if (A.out_param_hist && crank == 0) A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = p;
         }
-        if (A.out_param_hist && tid >= 7 && tid < 9 && !A.optimize_shapes)
+        if (A.out_param_hist && crank == 0 && tid >= 7 && tid < 9 && !A.optimize_shapes)
             A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = S.par[tid];
-        if (last) {
+        if (last && crank == 0) {
             if (A.out_eta_idx) for (int i = tid; i < kN; i += T) A.out_eta_idx[(size_t)obj * kN + i] = S.pj[i];
             if (A.out_grids) for (int i = tid; i < kG; i += T) {
                 A.out_grids[((size_t)obj * 2 + 0) * kG + i] = S.ge.slot[i].x;
@@ -452,8 +474,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         __syncthreads();
         SQ_MARK(S, tid, 6);
     }
-    if (A.out_cycles && tid < 12) A.out_cycles[(size_t)obj * 12 + tid] = S.cyc[tid];
-    if (tid < 9) {
+    if (A.out_cycles && crank == 0 && tid < 12) A.out_cycles[(size_t)obj * 12 + tid] = S.cyc[tid];
+    if (tid < 9 && crank == 0) {
         float p = S.par[tid];
         A.out_params[(size_t)obj * 9 + tid] = p;
         if (!isfinite(p)) atomicOr(&S.status, ODAM_SQ_ST_NONFINITE);
@@ -462,7 +484,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         if (A.out_grad) A.out_grad[(size_t)obj * 9 + tid] = S.grad[tid];
     }
     __syncthreads();
-    if (tid == 0 && A.out_status) A.out_status[obj] = S.status;
+    if (tid == 0 && A.out_status && S.status) atomicOr(&A.out_status[obj], S.status);  // zeroed by the host before the launch
 }
 
 // forward only: compute_ellipsoid_points for n objects, one CTA each
@@ -677,18 +699,24 @@ static int ensure_init(int device)
     return ODAM_SQ_OK;
 }
 
-struct LaunchCfg { int threads, max_slices, smem; };
+struct LaunchCfg { int threads, max_slices, smem, cluster; };
 
 // view statistics -> CTA size.  Small tracks get several point slices per view so that a CTA has >=4 warps.
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
                          int smem_optin, LaunchCfg &L)
 {
-    int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= 2 * sm_count ? 8 : 16);
+    int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= sm_count ? 8 : 16);
     if (max_slices < 1 || max_slices > 25) return ODAM_SQ_ERR_ARG;
+    // view-tiled clusters: when there are fewer objects than SMs, 2 or 4 CTAs (on different SMs) share an object
+    int cluster = opt ? opt->cluster : 0;
+    if (cluster == 0) cluster = (4 * n <= sm_count && mean_views >= 32) ? 4 : ((2 * n <= sm_count + 32 && mean_views >= 16) ? 2 : 1);
+    if (cluster != 1 && cluster != 2 && cluster != 4) return ODAM_SQ_ERR_ARG;
+    mean_views = std::max(1.0, mean_views / cluster);
+    max_views = (max_views + cluster - 1) / cluster;
     int threads = opt ? opt->threads : 0;
     if (threads == 0) {
         // throughput regime (many objects per SM): ~160 threads; latency regime (fewer CTAs than SMs): wider
-        int target = n >= 2 * sm_count ? 128 : 512;
+        int target = n * cluster >= 2 * sm_count ? 128 : 512;
         int v = std::max(1, (int)(mean_views + 0.5));
         int s = std::max(1, std::min(max_slices, target / v));
         threads = ((v * s + 31) / 32) * 32;
@@ -698,7 +726,7 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
     long smem = std::max<long>(items * 4 * 8, (long)kSpecBytes);  // dynamic part: phase-E results alias the B0 scratch
     if (smem + (long)sizeof(Smem) > smem_optin) return ODAM_SQ_ERR_CONFIG;
-    L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem;
+    L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem; L.cluster = cluster;
     return ODAM_SQ_OK;
 }
 
@@ -720,11 +748,18 @@ static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L
     OptArgs A = A0;
     A.max_slices = L.max_slices;
     A.beta1w = (float)(1.0 - 0.9); A.beta2 = (float)0.999; A.beta2w = (float)(1.0 - 0.999); A.eps = (float)1e-8;
+    A.cluster = L.cluster;
+    if (A.out_status) CU(cudaMemsetAsync(A.out_status, 0, sizeof(int32_t) * A.n, st));  // CTAs OR their flags in
     // every instantiation is capped at 64 registers/thread (1024 resident threads per SM worth of registers)
-    if (L.threads <= 256) sq_optimize_kernel<256><<<A.n, L.threads, L.smem, st>>>(A);
-    else if (L.threads <= 512) sq_optimize_kernel<512><<<A.n, L.threads, L.smem, st>>>(A);
-    else sq_optimize_kernel<1024><<<A.n, L.threads, L.smem, st>>>(A);
-    CU(cudaGetLastError());
+    void (*kern)(OptArgs) = L.threads <= 256 ? sq_optimize_kernel<256> : (L.threads <= 512 ? sq_optimize_kernel<512> : sq_optimize_kernel<1024>);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(A.n * L.cluster); cfg.blockDim = dim3(L.threads); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = L.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, kern, A));
     return ODAM_SQ_OK;
 }
 
@@ -776,7 +811,7 @@ const char *odam_sq_last_cuda_error(void) { return g_cuda_err; }
 int odam_sq_init(int device) { return ensure_init(device); }
 
 int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *opt, int *threads, int *smem_bytes,
-                         int *ctas_per_sm)
+                         int *ctas_per_sm, int *cluster)
 {
     if (!view_off || n <= 0) return ODAM_SQ_ERR_ARG;
     int maxv = 0;
@@ -785,6 +820,7 @@ int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *
     int rc = choose_launch(maxv, (double)(view_off[n] - view_off[0]) / n, n, opt, 148, 232448, L);
     if (rc) return rc;
     if (threads) *threads = L.threads;
+    if (cluster) *cluster = L.cluster;
     if (smem_bytes) *smem_bytes = L.smem;
     if (smem_bytes) *smem_bytes += (int)sizeof(Smem);
     if (ctas_per_sm) *ctas_per_sm = std::min({32, 2048 / L.threads, 65536 / (64 * L.threads), (233472 - 1024) / (L.smem + (int)sizeof(Smem) + 1024)});

@@ -51,11 +51,11 @@ def test_argument_validation_without_gpu(lib):
     a = np.zeros(3, np.float32)
     p = a.ctypes.data_as(ctypes.c_void_p)
     assert lib.odam_sq_sample_on_batch_host(p, p, p, p, 1, 1, 999, 201, 0, 0) == -1   # only N=1000 / 201 / seed 0
-    th, sm, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    th, sm, c, cl = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     voff = np.array([0, 20, 40], np.int32)
     assert lib.odam_sq_query_launch(voff.ctypes.data_as(ctypes.c_void_p), 2, None, ctypes.byref(th), ctypes.byref(sm),
-                                    ctypes.byref(c)) == 0
-    assert th.value % 32 == 0 and 32 <= th.value <= 1024 and sm.value > 0 and c.value >= 1
+                                    ctypes.byref(c), ctypes.byref(cl)) == 0
+    assert th.value % 32 == 0 and 32 <= th.value <= 1024 and sm.value > 0 and c.value >= 1 and cl.value in (1, 2, 4)
 
 
 def test_no_gpu_means_loud_failure_not_fallback(lib):

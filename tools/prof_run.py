@@ -21,6 +21,7 @@ ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--max-slices", type=int, default=0)
 ap.add_argument("--launches", type=int, default=2)
 ap.add_argument("--cycles", action="store_true")
+ap.add_argument("--cluster", type=int, default=0)
 a = ap.parse_args()
 c = synthetic.CONFIGS[a.config]
 scene = synthetic.make_scene(a.objects or c["n_objects"], c["n_views"], seed=a.config, device="cuda:0")
@@ -31,7 +32,7 @@ out = None
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.launches + 1)]
 ev[0].record()
 for k in range(a.launches):
-    out = api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out)
+    out = api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cluster=a.cluster)
     ev[k + 1].record()
 torch.cuda.synchronize()
 units = float(tracks.total_views) * iters
@@ -42,7 +43,7 @@ for k in range(a.launches):
 print("flagged", int((out["status"].cpu() & 3 != 0).sum()))
 if a.cycles:
     cyc = torch.zeros((tracks.n, 12), dtype=torch.int64, device="cuda:0")
-    api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc)
+    api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc, cluster=a.cluster)
     torch.cuda.synchronize()
     c = cyc.cpu().numpy().astype(float) / iters
     names = ["A derive", "B eta walk", "D points", "E project", "F backward", "G reduce+loss", "Adam", "C cdf+patch",
