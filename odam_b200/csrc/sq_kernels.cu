@@ -37,7 +37,7 @@ constexpr int kRed = 13;  // 9 gradients + 4 side sums
 struct alignas(16) Smem {
     float px[kNPad], py[kNPad], pz[kNPad];  // world points, SoA
     GridTab ge, go;
-    float cdf[kGPad];
+    alignas(16) float cdf[kGPad];
     uint8_t pj[kNPad];                      // eta-grid index of each sample
     float red[kMaxWarps][kRed + 3];
     float xred[2][kMaxCluster][kRed + 3];   // per-CTA partial sums exchanged through DSMEM, double-buffered by iteration parity
@@ -73,31 +73,34 @@ struct OptArgs {
     long long *out_cycles;
 };
 
-// phases A-D: parameters in S.par -> 1000 world points in S.px/py/pz (+ S.pj, grids)
+// phase A: what the sampler and the surface need of parameter `k` (one lane per parameter), plus the per-iteration
+// resets of the sampler state (lane 9).  Runs once before the first iteration and then fused with the Adam update.
+__device__ __forceinline__ void derive_param(Smem &S, int k)
+{
+    Pose &P = S.pose;
+    const float p = S.par[k];
+    if (k < 3) P.t[k] = p;
+    else if (k == 3) {
+        double sd, cd;
+        sq_sincos_pi(p, sd, cd);  // yaw: correctly rounded cos/sin for |angle| < ~1e5 rad
+        P.cz = (float)cd; P.sz = (float)sd;
+    } else if (k < 7) P.a[k - 4] = __fmul_rn(p, p);
+    else if (k < 9) {
+        float sg = (float)(1.0 / (1.0 + exp(-(double)p)));  // torch.sigmoid, correctly rounded
+        P.sig[k - 7] = sg;
+        P.e[k - 7] = __fadd_rn(__fmul_rn(sg, 1.4f), 0.2f);
+    } else if (k == 9) {
+        S.bad[0] = 0; S.bad[1] = 0;
+        S.ge.fix_lo = S.ge.count; S.go.fix_lo = S.go.count;
+        S.ge.changed = 0; S.go.changed = 0;
+    }
+}
+
+// phases B-D: derived quantities in S.pose -> 1000 world points in S.px/py/pz (+ S.pj, grids)
 __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid, int nthreads, bool have_prev)
 {
     const int warp = tid >> 5, lane = tid & 31;
     const int nwarps = nthreads >> 5;
-    // ---- A ---- (six lanes, one derived quantity each)
-    {
-        Pose &P = S.pose;
-        if (tid < 3) { P.a[tid] = __fmul_rn(S.par[4 + tid], S.par[4 + tid]); P.t[tid] = S.par[tid]; }
-        else if (tid < 5) {
-            const int k = tid - 3;
-            float sg = (float)(1.0 / (1.0 + exp(-(double)S.par[7 + k])));  // torch.sigmoid, correctly rounded
-            P.sig[k] = sg;
-            P.e[k] = __fadd_rn(__fmul_rn(sg, 1.4f), 0.2f);
-        } else if (tid == 5) {
-            double sd, cd;
-            sq_sincos_pi(S.par[3], sd, cd);  // yaw: correctly rounded cos/sin for |angle| < ~1e5 rad
-            P.cz = (float)cd; P.sz = (float)sd;
-            S.bad[0] = 0; S.bad[1] = 0;
-            S.ge.fix_lo = S.ge.count; S.go.fix_lo = S.go.count;
-            S.ge.changed = 0; S.go.changed = 0;
-        }
-    }
-    __syncthreads();
-    SQ_MARK(S, tid, 0);
     // ---- B0: node pool of the previous tree -> powers, split ratios, slots (all threads) ----
     const float pi = 3.14159274101257324f;       // (float)acos(-1), sampling.cpp:14
     const float pi_2 = __fmul_rn(pi, 0.5f);      // pi/2, :15
@@ -277,6 +280,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     __syncthreads();
 
     const float invV = Vall > 0 ? __fdiv_rn(1.f, (float)Vall) : 0.f;
+    if (tid < 10) derive_param(S, tid);
+    __syncthreads();
 
     for (int it = 0; it < A.n_iters; it++) {
         sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, T, it > 0);
@@ -419,37 +424,40 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             }
         }
         __syncthreads();
-        if (tid == 0) {
+        // ---- G: gradient of parameter k = tid (+ prior), Adam, derived quantities for the next iteration; the loss
+        // on lane 9.  (torch/optim/adam.py _single_tensor_adam; roundings as probed against torch's CPU kernels)
+        if (tid < 9) {
+            float g = S.red[0][tid];
+            if (A.prior && tid >= 4 && tid < 7) {  // d/ds of 20 (s0-s)^T A (s0-s)  (sq_libs.py:463-466)
+                const int r = tid - 4;
+                float sym = 0.f;
+                for (int cc = 0; cc < 3; cc++)
+                    sym = __fmaf_rn(S.prior[3 * r + cc] + S.prior[3 * cc + r], S.s0[cc] - S.par[4 + cc], sym);
+                g += -20.f * sym;
+            }
+            if (tid >= 7 && !A.optimize_shapes) g = 0.f;
+            S.grad[tid] = g;
+            if (!isfinite(g)) atomicOr(&S.status, ODAM_SQ_ST_NONFINITE);
+        }
+        if (tid == 9) {
             // loss = sum over sides of mean over ALL views (sq_libs.py:428-429) + prior (:463-466)
             float loss = 0.f;
-            for (int sd = 0; sd < 4; sd++) loss = __fadd_rn(loss, __fdiv_rn(S.red[0][9 + sd], (float)Vall));
-            float g[9];
-            for (int k = 0; k < 9; k++) g[k] = S.red[0][k];
+            for (int sd2 = 0; sd2 < 4; sd2++) loss = __fadd_rn(loss, __fdiv_rn(S.red[0][9 + sd2], (float)Vall));
             if (A.prior) {
-                float d0 = S.s0[0] - S.par[4], d1 = S.s0[1] - S.par[5], d2 = S.s0[2] - S.par[6];
-                float dd[3] = {d0, d1, d2};
+                float dd[3] = {S.s0[0] - S.par[4], S.s0[1] - S.par[5], S.s0[2] - S.par[6]};
                 float q3 = 0.f;
                 for (int r = 0; r < 3; r++) {
-                    float row = 0.f, sym = 0.f;
-                    for (int cc = 0; cc < 3; cc++) {
-                        row = __fmaf_rn(S.prior[3 * r + cc], dd[cc], row);
-                        sym = __fmaf_rn(S.prior[3 * r + cc] + S.prior[3 * cc + r], dd[cc], sym);
-                    }
+                    float row = 0.f;
+                    for (int cc = 0; cc < 3; cc++) row = __fmaf_rn(S.prior[3 * r + cc], dd[cc], row);
                     q3 = __fmaf_rn(dd[r], row, q3);
-                    g[4 + r] += -20.f * sym;
                 }
                 loss = __fadd_rn(loss, __fmul_rn(q3, 20.f));
             }
-            if (!A.optimize_shapes) { g[7] = 0.f; g[8] = 0.f; }
             if (crank == 0) A.out_loss[(size_t)obj * A.n_iters + it] = loss;
-            bool finite = isfinite(loss);
-            for (int k = 0; k < 9; k++) { S.grad[k] = g[k]; finite = finite && isfinite(g[k]); }
-            if (!finite) S.status |= ODAM_SQ_ST_NONFINITE;
-            if (S.bad[0] | S.bad[1]) S.status |= ODAM_SQ_ST_SAMPLER;
+            if (!isfinite(loss)) atomicOr(&S.status, ODAM_SQ_ST_NONFINITE);
+            if (S.bad[0] | S.bad[1]) atomicOr(&S.status, ODAM_SQ_ST_SAMPLER);
         }
-        __syncthreads();
-        SQ_MARK(S, tid, 5);
-        // Adam (torch/optim/adam.py _single_tensor_adam; roundings as probed against torch's CPU kernels)
+        __syncwarp();  // lanes 4..6 and 9 read the scales before lanes 4..6 update them
         if (tid < (A.optimize_shapes ? 9 : 7)) {
             float g = S.grad[tid], m = S.m[tid], v = S.v[tid], p = S.par[tid];
             float alpha = A.adam_tab[it * 4 + (tid < 7 ? 0 : 1)];
@@ -462,6 +470,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             S.m[tid] = m; S.v[tid] = v; S.par[tid] = p;
             if (A.out_param_hist && crank == 0) A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = p;
         }
+        if (tid < 10) derive_param(S, tid);
         if (A.out_param_hist && crank == 0 && tid >= 7 && tid < 9 && !A.optimize_shapes)
             A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = S.par[tid];
         if (last && crank == 0) {
@@ -499,6 +508,8 @@ __global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int
         pool_init(S.ge, pi_2, -pi_2);
         pool_init(S.go, pi, -pi);
     }
+    __syncthreads();
+    if (tid < 10) derive_param(S, tid);
     __syncthreads();
     sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
     for (int i = tid; i < kN; i += blockDim.x) {
@@ -551,6 +562,8 @@ __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, cons
         pool_init(S.ge, pi_2, -pi_2);
         pool_init(S.go, pi, -pi);
     }
+    __syncthreads();
+    if (tid < 10) derive_param(S, tid);
     __syncthreads();
     sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
     const int v_begin = view_off[obj], V = view_off[obj + 1] - v_begin;

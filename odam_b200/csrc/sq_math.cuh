@@ -89,25 +89,41 @@ SQ_HD void sq_sincos_pi(float theta, double &s, double &c)
     }
 }
 
+// Taylor coefficients 1/13! .. 1/2! of exp, then ln2 split and log2(e).  On the device they sit in constant
+// memory so that every DFMA takes its coefficient as a c[bank][offset] operand (an immediate double costs two
+// extra issue slots per use).
+#define SQ_EXP_COEFS                                                                                          \
+    {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,   \
+     1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,                                       \
+     6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.44269504088896338700e+00, 0.0}
+#ifdef __CUDACC__
+__constant__ double kSqExpC[16] = SQ_EXP_COEFS;
+#endif
+static const double kSqExpH[16] = SQ_EXP_COEFS;
+#ifdef __CUDA_ARCH__
+#define SQ_EC(i) kSqExpC[i]
+#else
+#define SQ_EC(i) kSqExpH[i]
+#endif
+
 // exp(y) for -700 < y <= 0:  y = k ln2 + r, |r| <= ln2/2, Taylor to r^13, scaled by 2^k through the exponent field
 SQ_HD double sq_exp_neg(double y)
 {
-    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
-    const double kf = rint(y * 1.44269504088896338700e+00);
-    double r = sq_fma(-kf, ln2_hi, y);
-    r = sq_fma(-kf, ln2_lo, r);
-    double e = 1.0 / 6227020800.0;
-    e = sq_fma(e, r, 1.0 / 479001600.0);
-    e = sq_fma(e, r, 1.0 / 39916800.0);
-    e = sq_fma(e, r, 1.0 / 3628800.0);
-    e = sq_fma(e, r, 1.0 / 362880.0);
-    e = sq_fma(e, r, 1.0 / 40320.0);
-    e = sq_fma(e, r, 1.0 / 5040.0);
-    e = sq_fma(e, r, 1.0 / 720.0);
-    e = sq_fma(e, r, 1.0 / 120.0);
-    e = sq_fma(e, r, 1.0 / 24.0);
-    e = sq_fma(e, r, 1.0 / 6.0);
-    e = sq_fma(e, r, 0.5);
+    const double kf = rint(y * SQ_EC(14));
+    double r = sq_fma(-kf, SQ_EC(12), y);
+    r = sq_fma(-kf, SQ_EC(13), r);
+    double e = SQ_EC(0);
+    e = sq_fma(e, r, SQ_EC(1));
+    e = sq_fma(e, r, SQ_EC(2));
+    e = sq_fma(e, r, SQ_EC(3));
+    e = sq_fma(e, r, SQ_EC(4));
+    e = sq_fma(e, r, SQ_EC(5));
+    e = sq_fma(e, r, SQ_EC(6));
+    e = sq_fma(e, r, SQ_EC(7));
+    e = sq_fma(e, r, SQ_EC(8));
+    e = sq_fma(e, r, SQ_EC(9));
+    e = sq_fma(e, r, SQ_EC(10));
+    e = sq_fma(e, r, SQ_EC(11));
     e = sq_fma(e, r, 1.0);
     e = sq_fma(e, r, 1.0);
     const int k = (int)kf;  // never subnormal on the caller's domain
