@@ -86,7 +86,9 @@ __device__ __forceinline__ void derive_param(Smem &S, int k)
         P.cz = (float)cd; P.sz = (float)sd;
     } else if (k < 7) P.a[k - 4] = __fmul_rn(p, p);
     else if (k < 9) {
-        float sg = (float)(1.0 / (1.0 + exp(-(double)p)));  // torch.sigmoid, correctly rounded
+        // torch.sigmoid, correctly rounded: t = exp(-|p|) in (0, 1], sigma = 1/(1+t) or t/(1+t)
+        const double t = p > -700.f && p < 700.f ? sq_exp_neg(-fabs((double)p)) : 0.0;
+        float sg = (float)((p >= 0.f ? 1.0 : t) / (1.0 + t));
         P.sig[k - 7] = sg;
         P.e[k - 7] = __fadd_rn(__fmul_rn(sg, 1.4f), 0.2f);
     } else if (k == 9) {
@@ -718,7 +720,7 @@ struct LaunchCfg { int threads, max_slices, smem, cluster; };
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
                          int smem_optin, LaunchCfg &L)
 {
-    int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= sm_count ? 8 : 16);
+    int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= sm_count ? 8 : 25);
     if (max_slices < 1 || max_slices > 25) return ODAM_SQ_ERR_ARG;
     // view-tiled clusters: when there are fewer objects than SMs, 2 or 4 CTAs (on different SMs) share an object
     int cluster = opt ? opt->cluster : 0;

@@ -46,8 +46,8 @@ if a.cycles:
     api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc, cluster=a.cluster)
     torch.cuda.synchronize()
     c = cyc.cpu().numpy().astype(float) / iters
-    names = ["A derive", "B eta walk", "D points", "E project", "F backward", "G reduce+loss", "Adam", "C cdf+patch",
-             "B0 powers (+barrier)", "B0 ratios (+barrier)", "wait for omega warp", "-"]
+    names = ["-", "B fix-up walk (eta)", "D points", "E project", "F backward + warp reduce", "-", "G reduce (+cluster), Adam, derive", "C cdf",
+             "B0 powers (+barrier)", "B0 ratios + placement", "wait for omega warp", "-"]
     print("mean SM cycles per iteration per object (thread 0's view):")
     for k in range(11):
         print(f"  {names[k]:30s} {c[:, k].mean():9.0f}  ({c[:, k].mean() / c.sum(1).mean():5.1%})")
