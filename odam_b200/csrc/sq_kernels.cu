@@ -30,7 +30,6 @@ namespace cg = cooperative_groups;
 
 namespace odam {
 
-constexpr int kMaxWarps = 32;
 constexpr int kMaxCluster = 4;   // CTAs per object (view-tiled thread-block cluster)
 constexpr int kRed = 13;  // 9 gradients + 4 side sums
 
@@ -39,8 +38,8 @@ struct alignas(16) Smem {
     GridTab ge, go;
     alignas(16) float cdf[kGPad];
     uint8_t pj[kNPad];                      // eta-grid index of each sample
-    float red[kMaxWarps][kRed + 3];
     float xred[2][kMaxCluster][kRed + 3];   // per-CTA partial sums exchanged through DSMEM, double-buffered by iteration parity
+    alignas(8) uint64_t xbar[2];            // one mbarrier per buffer: completes when all C*13 floats have landed
     float par[12], m[12], v[12], s0[4], grad[12], prior[12];
     Pose pose;
     int status;
@@ -63,7 +62,7 @@ constexpr size_t kFwdSmem = kSpecBytes;  // forward-only kernels: dynamic part =
 struct OptArgs {
     const float *init; const int32_t *cls; const int32_t *view_off;
     const float *Ms; const float *box; const uint8_t *mask; const float *prior;
-    int n, n_iters, optimize_shapes, max_slices, cluster;
+    int n, n_iters, optimize_shapes, max_slices, cluster, red_offset;
     const float *adam_tab;  // [n_iters][4]: -lr/bc1, -lr_shape/bc1, sqrt(bc2), unused
     float beta1w, beta2, beta2w, eps;
     const float *m0, *v0, *s0;
@@ -258,6 +257,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     const int V = v_obj + (Vall * (crank + 1)) / C - v_begin;   // this CTA's views
     // per-item results live after the fixed part of shared memory
     float *ext_val = reinterpret_cast<float *>(scratch_raw);
+    // cross-warp reduction scratch sits behind the per-item area (its size depends on the CTA size, not on 32 warps)
+    float(*red)[kRed + 3] = reinterpret_cast<float(*)[kRed + 3]>(scratch_raw + A.red_offset);
 
     int slices = V > 0 ? T / V : 1;
     slices = max(1, min(slices, A.max_slices));
@@ -278,8 +279,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         const float pi = 3.14159274101257324f, pi_2 = __fmul_rn(pi, 0.5f);
         pool_init(S.ge, pi_2, -pi_2);
         pool_init(S.go, pi, -pi);
+        if (C > 1) {
+            mbar_init(&S.xbar[0], 1);
+            mbar_init(&S.xbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
+    if (C > 1) cg::this_cluster().sync();  // every CTA of the cluster is resident and its barriers are initialised
 
     const float invV = Vall > 0 ? __fdiv_rn(1.f, (float)Vall) : 0.f;
     if (tid < 10) derive_param(S, tid);
@@ -403,33 +410,33 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             }
             if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < kRed; k++) S.red[warp][k] = acc[k];
+                for (int k = 0; k < kRed; k++) red[warp][k] = acc[k];
             }
         }
         __syncthreads();
         SQ_MARK(S, tid, 4);
         if (tid < kRed) {
             float x = 0.f;
-            for (int wi = 0; wi < nred; wi++) x += S.red[wi][tid];
-            S.red[0][tid] = x;
-            if (C > 1) {  // hand this CTA's partial to every CTA of the cluster (including itself)
-                cg::cluster_group cl = cg::this_cluster();
-                for (int r = 0; r < C; r++) *cl.map_shared_rank(&S.xred[it & 1][crank][tid], r) = x;
-            }
-        }
-        if (C > 1) {
-            cg::this_cluster().sync();
-            if (tid < kRed) {  // same rank order in every CTA -> identical sums -> identical Adam steps
-                float x = 0.f;
-                for (int r = 0; r < C; r++) x += S.xred[it & 1][r][tid];
-                S.red[0][tid] = x;
+            for (int wi = 0; wi < nred; wi++) x += red[wi][tid];
+            red[0][tid] = x;
+            if (C > 1) {
+                // hand this CTA's partial to every CTA of the cluster (including itself): asynchronous remote stores
+                // that complete on the receiver's mbarrier; buffers and barriers alternate with the iteration parity
+                const int pb = it & 1;
+                if (tid == 0) mbar_arrive_expect_tx(&S.xbar[pb], (uint32_t)(C * kRed * sizeof(float)));
+                const uint32_t dst = smem_u32(&S.xred[pb][crank][tid]), bar = smem_u32(&S.xbar[pb]);
+                for (int r = 0; r < C; r++) st_async_f32(mapa_u32(dst, r), x, mapa_u32(bar, r));
+                mbar_wait(&S.xbar[pb], (uint32_t)((it >> 1) & 1));
+                x = 0.f;  // same rank order in every CTA -> identical sums -> identical Adam steps
+                for (int r = 0; r < C; r++) x += S.xred[pb][r][tid];
+                red[0][tid] = x;
             }
         }
         __syncthreads();
         // ---- G: gradient of parameter k = tid (+ prior), Adam, derived quantities for the next iteration; the loss
         // on lane 9.  (torch/optim/adam.py _single_tensor_adam; roundings as probed against torch's CPU kernels)
         if (tid < 9) {
-            float g = S.red[0][tid];
+            float g = red[0][tid];
             if (A.prior && tid >= 4 && tid < 7) {  // d/ds of 20 (s0-s)^T A (s0-s)  (sq_libs.py:463-466)
                 const int r = tid - 4;
                 float sym = 0.f;
@@ -444,7 +451,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         if (tid == 9) {
             // loss = sum over sides of mean over ALL views (sq_libs.py:428-429) + prior (:463-466)
             float loss = 0.f;
-            for (int sd2 = 0; sd2 < 4; sd2++) loss = __fadd_rn(loss, __fdiv_rn(S.red[0][9 + sd2], (float)Vall));
+            for (int sd2 = 0; sd2 < 4; sd2++) loss = __fadd_rn(loss, __fdiv_rn(red[0][9 + sd2], (float)Vall));
             if (A.prior) {
                 float dd[3] = {S.s0[0] - S.par[4], S.s0[1] - S.par[5], S.s0[2] - S.par[6]};
                 float q3 = 0.f;
@@ -496,6 +503,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     }
     __syncthreads();
     if (tid == 0 && A.out_status && S.status) atomicOr(&A.out_status[obj], S.status);  // zeroed by the host before the launch
+    if (C > 1) cg::this_cluster().sync();  // no CTA exits while a peer may still store into its shared memory
 }
 
 // forward only: compute_ellipsoid_points for n objects, one CTA each
@@ -714,7 +722,7 @@ static int ensure_init(int device)
     return ODAM_SQ_OK;
 }
 
-struct LaunchCfg { int threads, max_slices, smem, cluster; };
+struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset; };
 
 // view statistics -> CTA size.  Small tracks get several point slices per view so that a CTA has >=4 warps.
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
@@ -739,9 +747,10 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     }
     if (threads % 32 || threads < 32 || threads > 1024) return ODAM_SQ_ERR_ARG;
     long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
-    long smem = std::max<long>(items * 4 * 8, (long)kSpecBytes);  // dynamic part: phase-E results alias the B0 scratch
+    long red_offset = std::max<long>(items * 4 * 8, (long)kSpecBytes);  // phase-E results alias the B0 scratch
+    long smem = red_offset + (threads / 32) * (kRed + 3) * 4;            // + cross-warp reduction rows
     if (smem + (long)sizeof(Smem) > smem_optin) return ODAM_SQ_ERR_CONFIG;
-    L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem; L.cluster = cluster;
+    L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem; L.cluster = cluster; L.red_offset = (int)red_offset;
     return ODAM_SQ_OK;
 }
 
@@ -764,6 +773,7 @@ static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L
     A.max_slices = L.max_slices;
     A.beta1w = (float)(1.0 - 0.9); A.beta2 = (float)0.999; A.beta2w = (float)(1.0 - 0.999); A.eps = (float)1e-8;
     A.cluster = L.cluster;
+    A.red_offset = L.red_offset;
     if (A.out_status) CU(cudaMemsetAsync(A.out_status, 0, sizeof(int32_t) * A.n, st));  // CTAs OR their flags in
     // every instantiation is capped at 64 registers/thread (1024 resident threads per SM worth of registers)
     void (*kern)(OptArgs) = L.threads <= 256 ? sq_optimize_kernel<256> : (L.threads <= 512 ? sq_optimize_kernel<512> : sq_optimize_kernel<1024>);
