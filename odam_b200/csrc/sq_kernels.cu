@@ -492,6 +492,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         __syncthreads();
         SQ_MARK(S, tid, 6);
     }
+    if (tid == 0) S.cyc[11] = S.ge.rebuilds + S.go.rebuilds;  // slot 11: tree rebuilds (both grids)
+    __syncthreads();
     if (A.out_cycles && crank == 0 && tid < 12) A.out_cycles[(size_t)obj * 12 + tid] = S.cyc[tid];
     if (tid < 9 && crank == 0) {
         float p = S.par[tid];
