@@ -102,30 +102,24 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
 {
     const int warp = tid >> 5, lane = tid & 31;
     const int nwarps = nthreads >> 5;
-    // ---- B0: node pool of the previous tree -> powers, split ratios, slots (all threads) ----
+    // ---- B0 (eta grid): node pool of the previous tree -> powers, split ratios, slots (all threads) ----
     const float pi = 3.14159274101257324f;       // (float)acos(-1), sampling.cpp:14
     const float pi_2 = __fmul_rn(pi, 0.5f);      // pi/2, :15
+    const Pose &P = S.pose;
     {
-        const Pose &P = S.pose;
-        // the two grids are interleaved from opposite ends so that every warp gets a share of both
+        int bad0 = 0;
         pool_powers(S.ge, spec[0], P.e[0], g_logtab[0], pi_2, tid, nthreads);
-        pool_powers(S.go, spec[1], P.e[1], g_logtab[1], pi_2, nthreads - 1 - tid, nthreads);
+        __syncthreads();
+        pool_ratios(S.ge, spec[0], P.a[0], P.a[2], tid, nthreads);
+        __syncthreads();
+        pool_place(S.ge, spec[0], tid, nthreads, bad0);
+        if (bad0) S.bad[0] = 1;
         __syncthreads();
         SQ_MARK(S, tid, 8);
-        pool_ratios(S.ge, spec[0], P.a[0], P.a[2], tid, nthreads);
-        pool_ratios(S.go, spec[1], P.a[0], P.a[1], nthreads - 1 - tid, nthreads);
-        __syncthreads();
-        int bad0 = 0, bad1 = 0;
-        pool_place(S.ge, spec[0], tid, nthreads, bad0);
-        pool_place(S.go, spec[1], nthreads - 1 - tid, nthreads, bad1);
-        if (bad0) S.bad[0] = 1;
-        if (bad1) S.bad[1] = 1;
-        __syncthreads();
-        SQ_MARK(S, tid, 9);
     }
-    // ---- B, C: fix-up walk over new nodes (everything on the first iteration), then the CDF ----
-    {
-        const Pose &P = S.pose;
+    // ---- B, C: warp 0 finishes the eta grid (fix-up walk over new nodes -- everything on the first iteration)
+    // and runs the strictly serial CDF; meanwhile all other warps do the omega grid's B0 behind a named barrier.
+    if (nwarps > 1) {
         if (warp == 0) {
             int bad = 0;
             pool_walk(S.ge, spec[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);  // :183-190
@@ -133,12 +127,31 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
             build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                                // :191-199
             if (bad) S.bad[0] = 1;
             SQ_MARK(S, tid, 7);
+        } else {
+            const int t1 = tid - 32, n1 = nthreads - 32;
+            int bad1 = 0;
+            pool_powers(S.go, spec[1], P.e[1], g_logtab[1], pi_2, t1, n1);
+            asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
+            pool_ratios(S.go, spec[1], P.a[0], P.a[1], t1, n1);
+            asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
+            pool_place(S.go, spec[1], t1, n1, bad1);
+            asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
+            if (warp == 1) pool_walk(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad1);  // :202-209
+            if (bad1) S.bad[1] = 1;
         }
-        if (warp == (nwarps > 1 ? 1 : 0)) {
-            int bad = 0;
-            pool_walk(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad);     // :202-209
-            if (bad) S.bad[1] = 1;
-        }
+    } else {  // a single warp does everything in turn
+        int bad = 0, bad1 = 0;
+        pool_walk(S.ge, spec[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);
+        build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);
+        pool_powers(S.go, spec[1], P.e[1], g_logtab[1], pi_2, tid, nthreads);
+        __syncwarp();
+        pool_ratios(S.go, spec[1], P.a[0], P.a[1], tid, nthreads);
+        __syncwarp();
+        pool_place(S.go, spec[1], tid, nthreads, bad1);
+        __syncwarp();
+        pool_walk(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad1);
+        if (bad) S.bad[0] = 1;
+        if (bad1) S.bad[1] = 1;
     }
     __syncthreads();
     SQ_MARK(S, tid, 10);

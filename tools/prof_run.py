@@ -47,7 +47,7 @@ if a.cycles:
     torch.cuda.synchronize()
     c = cyc.cpu().numpy().astype(float) / iters
     names = ["-", "B fix-up walk (eta)", "D points", "E project", "F backward + warp reduce", "-", "G reduce (+cluster), Adam, derive", "C cdf",
-             "B0 powers (+barrier)", "B0 ratios + placement", "wait for omega warp", "-"]
+             "B0 eta (powers, ratios, placement)", "-", "wait for omega warps", "rebuilds (count)"]
     print("mean SM cycles per iteration per object (thread 0's view):")
     for k in range(11):
         print(f"  {names[k]:30s} {c[:, k].mean():9.0f}  ({c[:, k].mean() / c.sum(1).mean():5.1%})")
