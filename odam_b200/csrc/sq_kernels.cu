@@ -745,20 +745,26 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
 {
     int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= sm_count ? 8 : 25);
     if (max_slices < 1 || max_slices > 25) return ODAM_SQ_ERR_ARG;
-    // view-tiled clusters: when there are fewer objects than SMs, 2 or 4 CTAs (on different SMs) share an object
+    // view-tiled clusters: when there are fewer objects than SMs, 2 or 4 CTAs (on different SMs) share an object;
+    // long tracks (>= 128 views) are split in two in any case (finer load balance across SMs)
     int cluster = opt ? opt->cluster : 0;
-    if (cluster == 0) cluster = (4 * n <= sm_count && mean_views >= 32) ? 4 : ((2 * n <= sm_count + 32 && mean_views >= 16) ? 2 : 1);
+    if (cluster == 0)
+        cluster = (4 * n <= sm_count && mean_views >= 32) ? 4
+                  : (((2 * n <= sm_count + 32 && mean_views >= 16) || mean_views >= 128) ? 2 : 1);
     if (cluster != 1 && cluster != 2 && cluster != 4) return ODAM_SQ_ERR_ARG;
     mean_views = std::max(1.0, mean_views / cluster);
     max_views = (max_views + cluster - 1) / cluster;
     int threads = opt ? opt->threads : 0;
     if (threads == 0) {
-        // throughput regime (many objects per SM): ~160 threads; latency regime (fewer CTAs than SMs): wider
-        int target = n * cluster >= 2 * sm_count ? 128 : 512;
+        // measured on B200: in the throughput regime (several CTAs per SM) ~6.4 threads per view,
+        // 128..320; in the latency regime (fewer CTAs than SMs) a wide CTA with many point slices per view
         int v = std::max(1, (int)(mean_views + 0.5));
-        int s = std::max(1, std::min(max_slices, target / v));
-        threads = ((v * s + 31) / 32) * 32;
-        threads = std::max(64, std::min(1024, threads));
+        if (n * cluster >= 2 * sm_count) {
+            threads = std::min(320, std::max(128, ((int)(v * 6.4 + 31) / 32) * 32));
+        } else {
+            int s = std::max(1, std::min(max_slices, 512 / v));
+            threads = std::max(64, std::min(1024, ((v * s + 31) / 32) * 32));
+        }
     }
     if (threads % 32 || threads < 32 || threads > 1024) return ODAM_SQ_ERR_ARG;
     long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
