@@ -64,7 +64,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -251,7 +251,6 @@ def run_native(args):
     if rank == 0:
         clocks.start()
     step_ms, kern_ms, out = time_config(api, torch, dt, n_iters, args.steps, args.warmup, flush, dist, gath)
-    clk = clocks.stop() if rank == 0 else None
     tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
@@ -275,6 +274,7 @@ def run_native(args):
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    clk = clocks.stop() if rank == 0 else None   # sampled across the device-timed AND the e2e timed regions
     SV, n = tracks.total_views, tracks.n
     h2d = n * 36 + n * 4 + (n + 1) * 4 + SV * (48 + 16 + 4) + (288 if prior is not None else 0) + n_iters * 16
     d2h = n * 36 + n * n_iters * 4 + n * 4

@@ -663,14 +663,18 @@ static void host_uniforms(uint32_t seed, int n, float *out)
     }
 }
 
-// log|cosf(theta)|, log|sinf(theta)| at the dyadic angles of a D&C tree rooted at (ta, tb); heap-indexed.
+// libm's log2_inline of |cosf(theta)| and |sinf(theta)| (the first half of the reference's powf calls) at the dyadic
+// angles of a D&C tree rooted at (ta, tb); heap-indexed.  Evaluated with the same host+device code the kernels use.
+static double2 logs_at(float th)
+{
+    const float c = fabsf(sq_glibc_cosf(th)), s = fabsf(sq_glibc_sinf(th));
+    return make_double2(sq_glibc_log2(c), s == 0.f ? -1e300 : sq_glibc_log2(s));
+}
 static void gen_logtab(float ta, float tb, int pos, std::vector<double2> &tab)
 {
     if (pos >= kTabSize) return;
     const float th = (ta + tb) * 0.5f;
-    const float c = (float)cosl((long double)th), s = (float)sinl((long double)th);
-    tab[pos].x = (double)logl(fabsl((long double)c));
-    tab[pos].y = s == 0.f ? -1e300 : (double)logl(fabsl((long double)s));
+    tab[pos] = logs_at(th);
     gen_logtab(ta, th, 2 * pos, tab);
     gen_logtab(th, tb, 2 * pos + 1, tab);
 }
@@ -713,15 +717,11 @@ static int ensure_init(int device)
         const float pi = 3.14159274101257324f, pi_2 = pi * 0.5f;
         std::vector<double2> tab(2 * kTabSize, make_double2(0.0, 0.0));
         std::vector<double2> one(kTabSize, make_double2(0.0, 0.0));
-        auto endpoint = [](float th) {
-            const float c = (float)cosl((long double)th), s = (float)sinl((long double)th);
-            return make_double2((double)logl(fabsl((long double)c)), (double)logl(fabsl((long double)s)));
-        };
         gen_logtab(pi_2, -pi_2, 1, one);
-        one[0] = endpoint(pi_2);
+        one[0] = logs_at(pi_2);
         std::copy(one.begin(), one.end(), tab.begin());
         gen_logtab(pi, -pi, 1, one);
-        one[0] = endpoint(pi);
+        one[0] = logs_at(pi);
         std::copy(one.begin(), one.end(), tab.begin() + kTabSize);
         CU(cudaMemcpyToSymbol(g_logtab, tab.data(), sizeof(double2) * 2 * kTabSize));
     }
