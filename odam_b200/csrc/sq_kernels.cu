@@ -40,6 +40,7 @@ struct alignas(16) Smem {
     uint8_t pj[kNPad];                      // eta-grid index of each sample
     float xred[2][kMaxCluster][kRed + 3];   // per-CTA partial sums exchanged through DSMEM, double-buffered by iteration parity
     alignas(8) uint64_t xbar[2];            // one mbarrier per buffer: completes when all C*13 floats have landed
+    alignas(8) uint64_t tma_bar;            // completion of the one-off TMA staging of this CTA's views
     float par[12], m[12], v[12], s0[4], grad[12], prior[12];
     Pose pose;
     int status;
@@ -63,6 +64,7 @@ struct OptArgs {
     const float *init; const int32_t *cls; const int32_t *view_off;
     const float *Ms; const float *box; const uint8_t *mask; const float *prior;
     int n, n_iters, optimize_shapes, max_slices, cluster, red_offset;
+    int stage_offset, stage_views;   // >0: this many views per CTA fit the staging area at scratch + stage_offset
     const float *adam_tab;  // [n_iters][4]: -lr/bc1, -lr_shape/bc1, sqrt(bc2), unused
     float beta1w, beta2, beta2w, eps;
     const float *m0, *v0, *s0;
@@ -192,10 +194,13 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
     SQ_MARK(S, tid, 2);
 }
 
+template <bool kStaged>
 __device__ __forceinline__ void load_M(const float *Ms, int gv, float (&M)[12])
 {
     const float4 *p = reinterpret_cast<const float4 *>(Ms + (size_t)gv * 12);
-    float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+    float4 r0, r1, r2;
+    if (kStaged) { r0 = p[0]; r1 = p[1]; r2 = p[2]; }             // shared memory (staged by TMA)
+    else { r0 = __ldg(p); r1 = __ldg(p + 1); r2 = __ldg(p + 2); }  // global, read-only path
     M[0] = r0.x; M[1] = r0.y; M[2] = r0.z; M[3] = r0.w;
     M[4] = r1.x; M[5] = r1.y; M[6] = r1.z; M[7] = r1.w;
     M[8] = r2.x; M[9] = r2.y; M[10] = r2.z; M[11] = r2.w;
@@ -301,6 +306,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     __syncthreads();
     if (C > 1) cg::this_cluster().sync();  // every CTA of the cluster is resident and its barriers are initialised
 
+    // One-off staging of this CTA's camera matrices and boxes into shared memory by TMA bulk copies (when the launch
+    // reserved room: few, wide CTAs); masks are bytes at 4-byte granularity, copied by plain loads.
+    const bool staged = A.stage_views > 0 && V <= A.stage_views;
+    float *sMs = reinterpret_cast<float *>(scratch_raw + A.stage_offset);
+    float *sBox = sMs + (size_t)A.stage_views * 12;
+    uint8_t *sMask = reinterpret_cast<uint8_t *>(sBox + (size_t)A.stage_views * 4);
+    if (staged && V > 0) {
+        if (tid == 0) {
+            mbar_init(&S.tma_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_arrive_expect_tx(&S.tma_bar, (uint32_t)V * 64u);
+            tma_bulk_g2s(sMs, A.Ms + (size_t)v_begin * 12, (uint32_t)V * 48u, &S.tma_bar);
+            tma_bulk_g2s(sBox, A.box + (size_t)v_begin * 4, (uint32_t)V * 16u, &S.tma_bar);
+        }
+        for (int i = tid; i < V; i += T) reinterpret_cast<uint32_t *>(sMask)[i] = reinterpret_cast<const uint32_t *>(A.mask)[v_begin + i];
+        __syncthreads();
+        mbar_wait(&S.tma_bar, 0);
+    }
+    const float *Msrc = staged ? sMs : A.Ms + (size_t)v_begin * 12;
+    const float *Bsrc = staged ? sBox : A.box + (size_t)v_begin * 4;
+    const uint8_t *Ksrc = staged ? sMask : A.mask + (size_t)v_begin * 4;
+
     const float invV = Vall > 0 ? __fdiv_rn(1.f, (float)Vall) : 0.f;
     if (tid < 10) derive_param(S, tid);
     __syncthreads();
@@ -313,7 +340,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
         for (int item = tid; item < n_items; item += T) {
             int sl = item / V, v = item - sl * V;
             float M[12];
-            load_M(A.Ms, v_begin + v, M);
+            if (staged) load_M<true>(Msrc, v, M); else load_M<false>(Msrc, v, M);
             M[11] = __fadd_rn(M[11], 1e-6f);  // the reference's |z| + 1e-6, folded (see project_uv)
             int c0 = (sl * kNChunks) / slices, c1 = ((sl + 1) * kNChunks) / slices;
             float best[4];
@@ -344,8 +371,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
                 if (better) { best = b; cid = ext_arg[(sl * V + v) * 4 + sd]; }
             }
             int gv = v_begin + v;
-            float target = A.box[(size_t)gv * 4 + sd];
-            float mk = A.mask[(size_t)gv * 4 + sd] ? 1.f : 0.f;
+            float target = Bsrc[v * 4 + sd];
+            float mk = Ksrc[v * 4 + sd] ? 1.f : 0.f;
             // The scan ranks points with a 1-ulp reciprocal; the winner's coordinate is now re-evaluated with the
             // reference's own rounding sequence (k-ordered FMA chain of the CPU GEMM, IEEE division) so that the
             // loss carries the same fp32 noise as the reference's instead of an independent sample of it.
@@ -353,7 +380,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             float qx = 0.f, qy = 0.f, qz = 1.f, d = 1.f;
             int arg = -1;
             if (cid >= 0) {
-                load_M(A.Ms, gv, M);
+                if (staged) load_M<true>(Msrc, v, M); else load_M<false>(Msrc, v, M);
                 const float m11 = M[11];
                 M[11] = __fadd_rn(m11, 1e-6f);
                 arg = resolve_arg(S, M, cid, sd >= 2, best);
@@ -594,7 +621,7 @@ __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, cons
     const int v_begin = view_off[obj], V = view_off[obj + 1] - v_begin;
     for (int v = tid; v < V; v += blockDim.x) {
         float M[12];
-        load_M(Ms, v_begin + v, M);
+        load_M<false>(Ms, v_begin + v, M);
         float b0 = INFINITY, b1 = -INFINITY, b2 = INFINITY, b3 = -INFINITY;
         for (int i = 0; i < kN; i++) {
             float X = S.px[i], Y = S.py[i], Z = S.pz[i];
@@ -737,7 +764,7 @@ static int ensure_init(int device)
     return ODAM_SQ_OK;
 }
 
-struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset; };
+struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_offset, stage_views; };
 
 // view statistics -> CTA size.  Small tracks get several point slices per view so that a CTA has >=4 warps.
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
@@ -770,8 +797,13 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
     long red_offset = std::max<long>(items * 4 * 8, (long)kSpecBytes);  // phase-E results alias the B0 scratch
     long smem = red_offset + (threads / 32) * (kRed + 3) * 4;            // + cross-warp reduction rows
+    // latency regime (few, wide CTAs: shared memory is plentiful): stage each CTA's views by TMA, 68 bytes per view
+    long stage_offset = (smem + 15) & ~15L;
+    int stage_views = (n * cluster < 2 * sm_count && max_views <= 256) ? ((max_views + 3) & ~3) : 0;
+    if (stage_views) smem = stage_offset + (long)stage_views * 68;
     if (smem + (long)sizeof(Smem) > smem_optin) return ODAM_SQ_ERR_CONFIG;
     L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem; L.cluster = cluster; L.red_offset = (int)red_offset;
+    L.stage_offset = (int)stage_offset; L.stage_views = stage_views;
     return ODAM_SQ_OK;
 }
 
@@ -795,6 +827,7 @@ static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L
     A.beta1w = (float)(1.0 - 0.9); A.beta2 = (float)0.999; A.beta2w = (float)(1.0 - 0.999); A.eps = (float)1e-8;
     A.cluster = L.cluster;
     A.red_offset = L.red_offset;
+    A.stage_offset = L.stage_offset; A.stage_views = L.stage_views;
     if (A.out_status) CU(cudaMemsetAsync(A.out_status, 0, sizeof(int32_t) * A.n, st));  // CTAs OR their flags in
     // every instantiation is capped at 64 registers/thread (1024 resident threads per SM worth of registers)
     void (*kern)(OptArgs) = L.threads <= 256 ? sq_optimize_kernel<256> : (L.threads <= 512 ? sq_optimize_kernel<512> : sq_optimize_kernel<1024>);
