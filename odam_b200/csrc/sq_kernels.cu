@@ -249,6 +249,7 @@ __device__ __forceinline__ int resolve_arg(const Smem &S, const float (&M)[12], 
 {
     int found = -1;
     const int base = c * kChunk;
+#pragma unroll 4
     for (int h = kChunk - 1; h >= 0; h--) {
         float u, w;
         project_uv<true>(M, S.px[base + h], S.py[base + h], S.pz[base + h], u, w);
@@ -365,10 +366,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             // combine slices in index order; strict comparison keeps the first index on ties
             float best = ext_val[v * 4 + sd];
             int cid = ext_arg[v * 4 + sd];
-            for (int sl = 1; sl < slices; sl++) {
-                float b = ext_val[(sl * V + v) * 4 + sd];
-                bool better = (sd & 1) ? (b > best) : (b < best);
-                if (better) { best = b; cid = ext_arg[(sl * V + v) * 4 + sd]; }
+#pragma unroll 4
+            for (int sl = 1; sl < slices; sl++) {   // branch-free so that the loads of several slices are in flight
+                const float b = ext_val[(sl * V + v) * 4 + sd];
+                const int cb = ext_arg[(sl * V + v) * 4 + sd];
+                const bool better = (sd & 1) ? (b > best) : (b < best);
+                best = better ? b : best;
+                cid = better ? cb : cid;
             }
             int gv = v_begin + v;
             float target = Bsrc[v * 4 + sd];
