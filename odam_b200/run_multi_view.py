@@ -33,20 +33,41 @@ def bbox_to_lines(bbox, img_size, edge_threshold=EDGE_THRESHOLD):
 
 
 def stage_object(track, frame_ids, img_h, img_w):
-    """What run_multi_view.py:31-58 derives for one track: class, averaged pose, mean dims, and per usable frame
-    (index into frame_ids) the box lines."""
+    """What run_multi_view.py:31-58 derives for one track, vectorised over frames: class, averaged pose, mean dims,
+    and for every usable frame (index into frame_ids) the detected box sides with the 20 px border rule applied.
+    Returns box [Vvalid, 4] / mask [Vvalid, 4] directly in the C-ABI order x_min, x_max, y_min, y_max."""
     track = np.asarray(track)
+    frame_ids = np.asarray(frame_ids)
     obj_class = int(np.median(track[:, 1]))
     obj_frames = track[:, 0].astype(np.int32)
     t_wo = track[:, 9:12].mean(axis=0)
-    rows = [int(np.where(f == obj_frames)[0][0]) if f in obj_frames else -1 for f in frame_ids]
-    present = [(i, r) for i, r in enumerate(rows) if r >= 0]
-    R_mean = Rotation.from_matrix(np.stack([rotz(track[r, 12]) for _, r in present])).mean().as_matrix()
-    dims = np.mean(np.stack([track[r, 6:9] for _, r in present]), axis=0)
-    lines = {i: bbox_to_lines(track[r, 2:6].reshape(2, 2), (img_h, img_w)) for i, r in present}
-    valid = [i for i, _ in present if len(lines[i]) > 0]
-    return dict(obj_class=obj_class, t_wo=t_wo, R=R_mean, dims=dims, valid_frames=valid,
-                lines=[lines[i] for i in valid])
+    # first track row of every frame id (the reference takes np.where(...)[0][0])
+    uniq, first = np.unique(obj_frames, return_index=True)
+    pos = np.searchsorted(uniq, frame_ids)
+    pos_c = np.minimum(pos, len(uniq) - 1)
+    present = uniq[pos_c] == frame_ids
+    img_idx = np.nonzero(present)[0]
+    rows = first[pos_c[present]]
+    yaw = track[rows, 12]
+    c, s_ = np.cos(yaw), np.sin(yaw)
+    Rz = np.zeros((len(rows), 3, 3))
+    Rz[:, 0, 0], Rz[:, 0, 1], Rz[:, 1, 0], Rz[:, 1, 1], Rz[:, 2, 2] = c, -s_, s_, c, 1.0
+    R_mean = Rotation.from_matrix(Rz).mean().as_matrix()
+    dims = track[rows, 6:9].mean(axis=0)
+    bb = track[rows, 2:6]                                              # x_min, y_min, x_max, y_max (pixels)
+    box = np.stack([bb[:, 0], bb[:, 2], bb[:, 1], bb[:, 3]], axis=1)   # -> x_min, x_max, y_min, y_max
+    hi = np.array([img_w, img_w, img_h, img_h], np.float64) - EDGE_THRESHOLD
+    mask = (box > EDGE_THRESHOLD) & (box < hi)                         # quadric_helper.py:87-107
+    valid = mask.any(axis=1)                                           # run_multi_view.py:52-55
+    return dict(obj_class=obj_class, t_wo=t_wo, R=R_mean, dims=dims, valid_frames=img_idx[valid].tolist(),
+                box=np.where(mask[valid], box[valid], 0.0).astype(np.float32), mask=mask[valid].astype(np.uint8))
+
+
+def lines_of(stage):
+    """The reference's list-of-dicts form of a staged object's boxes (for SuperQuadricOptimizer.run)."""
+    names = ("x_min", "x_max", "y_min", "y_max")
+    return [{n: (np.array([1, 0, -float(b[k])]) if n[0] == "x" else np.array([0, 1, -float(b[k])]))
+             for k, n in enumerate(names) if m[k]} for b, m in zip(stage["box"], stage["mask"])]
 
 
 def optim_process(tracks, img_names, T_wcs, P_cws, img_h, img_w, K, representation, prior, n_iters, n_views,
@@ -64,7 +85,7 @@ def optim_process(tracks, img_names, T_wcs, P_cws, img_h, img_w, K, representati
         optimizers.append(o)
     run = [i for i, s in enumerate(staged) if len(s["valid_frames"]) >= n_views]  # :59-62 eligibility
     if run:
-        optimize_batch([optimizers[i] for i in run], [staged[i]["lines"] for i in run],
+        optimize_batch([optimizers[i] for i in run], [(staged[i]["box"], staged[i]["mask"]) for i in run],
                        [P_cws[staged[i]["valid_frames"]] for i in run], n_iters, device=device)
         pts = api.sample_points_host(np.stack([optimizers[i].Q_init.params() for i in run]), device=device)
     bboxes_qc = list(bboxes_dl)

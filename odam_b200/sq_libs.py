@@ -119,8 +119,11 @@ class SuperQuadricOptimizer:
     # -- packing ----------------------------------------------------------------------------------------
     def _pack(self, gt_lines, Ms):
         Ms = np.ascontiguousarray(np.asarray(Ms, np.float64).reshape(-1, 12), np.float32)  # torch.tensor(Ms).float()
-        box, mask = api.pack_lines(gt_lines)
-        if len(gt_lines) != Ms.shape[0]:
+        if isinstance(gt_lines, tuple):   # already packed (box[V,4] float32 pixels, mask[V,4]) by the batched call site
+            box, mask = np.ascontiguousarray(gt_lines[0], np.float32), np.ascontiguousarray(gt_lines[1], np.uint8)
+        else:
+            box, mask = api.pack_lines(gt_lines)
+        if len(box) != Ms.shape[0]:
             raise ValueError("one projection matrix per set of lines expected")
         return Ms, box, mask
 

@@ -132,8 +132,10 @@ def test_call_site_staging_matches_reference():
         assert np.allclose(s["t_wo"], G[f"t{t}_T_wo"][:3, 3]) and np.allclose(s["R"], G[f"t{t}_T_wo"][:3, :3])
         assert np.allclose(s["dims"], G[f"t{t}_dims"])
         assert np.array_equal(np.array(s["valid_frames"]), G[f"t{t}_valid"])
-        box, mask = api.pack_lines(s["lines"])
-        assert np.array_equal(mask, G[f"t{t}_mask"]) and np.allclose(box, G[f"t{t}_box"].astype(np.float32))
+        assert np.array_equal(s["mask"], G[f"t{t}_mask"]) and np.array_equal(s["box"], G[f"t{t}_box"].astype(np.float32))
+        from odam_b200.run_multi_view import lines_of
+        box, mask = api.pack_lines(lines_of(s))            # and through the reference's dict form
+        assert np.array_equal(mask, s["mask"]) and np.array_equal(box, s["box"])
         assert np.isclose(Rotation.from_matrix(s["R"]).as_euler("zxy")[0], float(G[f"t{t}_yaw"]))
         assert np.allclose(get_3d_box(s["dims"], s["R"], s["t_wo"]), G[f"t{t}_bbox_dl"])
     for k in range(6):
