@@ -191,7 +191,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, n_obj), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -337,7 +337,7 @@ def run_native(args):
             "objects_flagged": int((status & 3 != 0).sum()), "sweep": sweep}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_sequential(scene, tracks, prior, args.cpu_budget)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -350,6 +350,23 @@ def launch_info(api, tracks):
     _lib.check(_lib.load().odam_sq_query_launch(_lib.ptr(np.ascontiguousarray(tracks.view_off, np.int32)), tracks.n,
                                                 C.byref(o), C.byref(th), C.byref(sm), C.byref(cps), C.byref(cl)))
     return th.value, sm.value, cps.value, cl.value
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one), so fd 1
+    is pointed at stderr for the duration of the run and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
@@ -366,6 +383,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-iters", type=int, default=20)
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
