@@ -330,7 +330,7 @@ def run_native(args):
                                    f"prior={'on' if cfg['prior'] else 'off'} (per GPU; weak scaling)",
                        "objects_per_gpu": tracks.n, "views": int(views.max()), "iters": n_iters, "samples": 1000,
                        "l2": "256 MiB memset between timed steps (inputs are < L2)",
-                       "launch": dict(zip(("threads", "smem_bytes", "ctas_per_sm", "ctas_per_object"), launch_info(api, tracks)))},
+                       "launch": dict(zip(("threads", "smem_bytes", "ctas_per_sm", "ctas_per_object", "code_layout"), launch_info(api, tracks)))},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e2e_ms[0]), "steps": e2e_steps},
             "gpu_launches": args.steps, "roofline": roofline,
@@ -343,13 +343,8 @@ def run_native(args):
 
 
 def launch_info(api, tracks):
-    import ctypes as C
-    from odam_b200 import _lib
-    th, sm, cps, cl = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-    o = _lib.Options()
-    _lib.check(_lib.load().odam_sq_query_launch(_lib.ptr(np.ascontiguousarray(tracks.view_off, np.int32)), tracks.n,
-                                                C.byref(o), C.byref(th), C.byref(sm), C.byref(cps), C.byref(cl)))
-    return th.value, sm.value, cps.value, cl.value
+    q = api.query_launch(tracks.view_off)
+    return q["threads"], q["smem_bytes"], q["ctas_per_sm"], q["cluster"], q["code_layout"]
 
 
 _REAL_STDOUT = None

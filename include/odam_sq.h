@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ODAM_SQ_ABI_VERSION 1
+#define ODAM_SQ_ABI_VERSION 2
 #define ODAM_SQ_N_SAMPLES 1000 /* sq_libs.py:545  EqualDistanceSamplerSQ(1000) */
 #define ODAM_SQ_GRID 201       /* _sampler.pyx:423 buffer_size */
 #define ODAM_SQ_N_PARAMS 9
@@ -76,6 +76,10 @@ typedef struct odam_sq_options {
                                (2 or 4 when there are fewer objects than SMs)                                 */
     int max_views;          /* device-pointer entry only: max views of any object, if the caller knows it
                                (with threads != 0 this avoids reading view_off back to the host)         */
+    int code_layout;        /* 0 = auto.  1 = straight-line build of the kernel (16-point blocks, one copy of the sampler
+                               per grid: most ILP, for a CTA that has its SM to itself);  2 = compact build (4-point
+                               blocks, both grids through one copy: small instruction-cache footprint, for many CTAs
+                               per SM in different phases).  Same arithmetic, bit-identical results.        */
     /* teacher forcing (tests): start from a recorded optimiser state instead of a fresh one          */
     const float *m0;        /* [n][9] Adam exp_avg     (NULL = zeros)                                  */
     const float *v0;        /* [n][9] Adam exp_avg_sq  (NULL = zeros)                                  */
@@ -141,7 +145,7 @@ int odam_sq_fma_peak(int device, double *tflops);
 
 /* The launch configuration odam_sq_optimize would use (for benchmarks/logging). */
 int odam_sq_query_launch(const int32_t *view_off_host, int n, const odam_sq_options *opt,
-                         int *threads, int *smem_bytes, int *ctas_per_sm, int *cluster);
+                         int *threads, int *smem_bytes, int *ctas_per_sm, int *cluster, int *code_layout);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libodam_sq.so")
+# ODAM_SQ_LIB selects another build of the same library (A/B timing of kernel variants, tools/ab_build.sh)
+LIB_PATH = os.environ.get("ODAM_SQ_LIB") or os.path.join(HERE, "lib", "libodam_sq.so")
 
 REPR = {"super_quadric": 0, "cube": 1, "quadric": 2}
 ST_NONFINITE, ST_SAMPLER, ST_NO_VALID_PT = 1, 2, 4
@@ -21,6 +22,7 @@ EXPORTS = ("odam_sq_abi_version", "odam_sq_error_string", "odam_sq_last_cuda_err
 class Options(C.Structure):
     """odam_sq_options (include/odam_sq.h)."""
     _fields_ = [("threads", C.c_int), ("max_slices", C.c_int), ("cluster", C.c_int), ("max_views", C.c_int),
+                ("code_layout", C.c_int),
                 ("m0", C.c_void_p), ("v0", C.c_void_p), ("step0", C.c_int), ("s0", C.c_void_p),
                 ("out_m", C.c_void_p), ("out_v", C.c_void_p), ("out_grad", C.c_void_p), ("out_pred", C.c_void_p),
                 ("out_arg", C.c_void_p), ("out_eta_idx", C.c_void_p), ("out_grids", C.c_void_p),
@@ -56,7 +58,7 @@ def load():
         L.odam_sq_project_boxes_host.argtypes = [vp, vp, vp, ci, vp, ci]
         L.odam_sq_sample_on_batch_host.argtypes = [vp] * 4 + [ci] * 6
         L.odam_sq_fma_peak.argtypes = [ci, C.POINTER(C.c_double)]
-        L.odam_sq_query_launch.argtypes = [vp, ci, C.POINTER(Options)] + [C.POINTER(ci)] * 4
+        L.odam_sq_query_launch.argtypes = [vp, ci, C.POINTER(Options)] + [C.POINTER(ci)] * 5
         for f in EXPORTS:
             if getattr(L, f).restype is None:
                 pass

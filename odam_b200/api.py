@@ -108,9 +108,22 @@ def prior_table(path=None):
     return np.stack([np.asarray(pr[CLASS_MAPPER[c]], np.float64).astype(np.float32).reshape(9) for c in range(8)])
 
 
-def _options(n, SV, n_iters, threads, max_slices, m0, v0, step0, s0, extras, alloc, cluster=0):
+def query_launch(view_off, threads=0, max_slices=0, cluster=0, code_layout=0):
+    """The launch configuration the library would choose for these tracks (odam_sq_query_launch)."""
+    L = _lib.load()
+    view_off = np.ascontiguousarray(view_off, np.int32)
+    o = _lib.Options()
+    o.threads, o.max_slices, o.cluster, o.code_layout = int(threads), int(max_slices), int(cluster), int(code_layout)
+    th, sm, cps, cl, lay = (C.c_int() for _ in range(5))
+    _lib.check(L.odam_sq_query_launch(_lib.ptr(view_off), len(view_off) - 1, C.byref(o), C.byref(th), C.byref(sm),
+                                      C.byref(cps), C.byref(cl), C.byref(lay)))
+    return dict(threads=th.value, smem_bytes=sm.value, ctas_per_sm=cps.value, cluster=cl.value, code_layout=lay.value)
+
+
+def _options(n, SV, n_iters, threads, max_slices, m0, v0, step0, s0, extras, alloc, cluster=0, code_layout=0):
     o = _lib.Options()
     o.threads, o.max_slices, o.step0, o.cluster = int(threads), int(max_slices), int(step0), int(cluster)
+    o.code_layout = int(code_layout)
     keep = {}
     for name, arr, shape in (("m0", m0, (n, 9)), ("v0", v0, (n, 9)), ("s0", s0, (n, 3))):
         if arr is not None:
@@ -125,7 +138,8 @@ def _options(n, SV, n_iters, threads, max_slices, m0, v0, step0, s0, extras, all
 
 
 def optimize_host(tracks, prior=None, n_iters=200, representation="super_quadric", lr=0.01, lr_shape=0.1,
-                  device=0, threads=0, max_slices=0, m0=None, v0=None, step0=0, s0=None, extras=(), cluster=0):
+                  device=0, threads=0, max_slices=0, m0=None, v0=None, step0=0, s0=None, extras=(), cluster=0,
+                  code_layout=0):
     """Run the fused optimiser on packed host arrays.  Returns dict(params[n,9], loss[n,n_iters], status[n], ...extras).
 
     prior: None (no prior term) or an [8,9] float32 table (see prior_table()).
@@ -139,7 +153,7 @@ def optimize_host(tracks, prior=None, n_iters=200, representation="super_quadric
     def alloc(arr, shape, dtype=np.float32):
         return np.zeros(shape, dtype) if arr is None else np.ascontiguousarray(arr, dtype).reshape(shape)
 
-    o, keep = _options(n, SV, n_iters, threads, max_slices, m0, v0, step0, s0, extras, alloc, cluster)
+    o, keep = _options(n, SV, n_iters, threads, max_slices, m0, v0, step0, s0, extras, alloc, cluster, code_layout)
     for name, arr in keep.items():
         setattr(o, name, _lib.ptr(arr))
     init = f32c(tracks.init, (n, 9))
@@ -213,7 +227,7 @@ class DeviceTracks:
 
 
 def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr_shape=0.1, threads=0,
-                    max_slices=0, out=None, cycles=None, cluster=0):
+                    max_slices=0, out=None, cycles=None, cluster=0, code_layout=0):
     """Enqueue one fused launch on torch's current stream; returns dict of CUDA tensors (no sync)."""
     torch = dt.torch
     L = _lib.load()
@@ -222,13 +236,11 @@ def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr
                    loss=torch.empty((dt.n, n_iters), dtype=torch.float32, device=dt.device),
                    status=torch.empty((dt.n,), dtype=torch.int32, device=dt.device))
     o = _lib.Options()
-    o.cluster, o.max_slices = int(cluster), int(max_slices)
-    if threads == 0:  # choose on the host from the host copy of view_off (avoids the library's D2H read-back)
-        th, sm, cps, cl = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        _lib.check(L.odam_sq_query_launch(_lib.ptr(dt.view_off_host), dt.n, C.byref(o), C.byref(th), C.byref(sm),
-                                          C.byref(cps), C.byref(cl)))
-        threads = th.value
-    o.threads, o.max_slices = int(threads), int(max_slices)
+    if threads == 0 or cluster == 0 or code_layout == 0:
+        # choose on the host from the host copy of view_off (avoids the library's D2H read-back)
+        q = query_launch(dt.view_off_host, threads, max_slices, cluster, code_layout)
+        threads, cluster, code_layout = q["threads"], q["cluster"], q["code_layout"]
+    o.threads, o.max_slices, o.cluster, o.code_layout = int(threads), int(max_slices), int(cluster), int(code_layout)
     o.max_views = int(np.diff(dt.view_off_host).max()) if dt.n else 0
     if cycles is not None:  # int64 CUDA tensor [n, 8]: per-phase SM cycles (diagnostics)
         o.out_cycles = cycles.data_ptr()

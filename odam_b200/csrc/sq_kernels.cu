@@ -100,30 +100,60 @@ __device__ __forceinline__ void derive_param(Smem &S, int k)
 }
 
 // phases B-D: derived quantities in S.pose -> 1000 world points in S.px/py/pz (+ S.pj, grids)
+// kCompact: both grids through one copy of the B0/walk code (see the loop below); otherwise one specialised copy each.
+template <bool kCompact>
 __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid, int nthreads, bool have_prev)
 {
     const int warp = tid >> 5, lane = tid & 31;
-    const int nwarps = nthreads >> 5;
-    // ---- B0 (eta grid): node pool of the previous tree -> powers, split ratios, slots (all threads) ----
+    // ---- B0: node pool of the previous tree -> powers, split ratios, slots; B: fix-up walk; C: CDF ----
+    // (every kernel here runs at least two warps)
     const float pi = 3.14159274101257324f;       // (float)acos(-1), sampling.cpp:14
     const float pi_2 = __fmul_rn(pi, 0.5f);      // pi/2, :15
     const Pose &P = S.pose;
-    {
-        int bad0 = 0;
+    if constexpr (kCompact) {
+        // Both grids run through ONE copy of the code (instruction-cache footprint): pass 0 is the eta grid with every
+        // thread, pass 1 the omega grid with warps >= 1 behind named barrier 1 -- meanwhile warp 0 finishes the eta
+        // grid (fix-up walk over new nodes -- everything on the first iteration -- then the strictly serial CDF).
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            GridTab &g = pass ? S.go : S.ge;
+            GridSpec &sp = spec[pass];
+            const float a2 = pass ? P.a[1] : P.a[2];
+            int bad = 0;
+            if (warp >= pass) {
+                const int t = tid - 32 * pass, n = nthreads - 32 * pass;
+                pool_powers(g, sp, P.e[pass], g_logtab[pass], pi_2, t, n);
+                asm volatile("bar.sync %0, %1;" ::"r"(pass), "r"(n) : "memory");
+                pool_ratios(g, sp, P.a[0], a2, t, n);
+                asm volatile("bar.sync %0, %1;" ::"r"(pass), "r"(n) : "memory");
+                pool_place(g, sp, t, n, bad);
+                asm volatile("bar.sync %0, %1;" ::"r"(pass), "r"(n) : "memory");
+                if (pass == 0) SQ_MARK(S, tid, 8);
+            }
+            if (warp == pass) {  // the grid's serial tail belongs to one warp: sampling.cpp:183-190 / :202-209
+                const float tb = pass ? pi : pi_2;
+                pool_walk(g, sp, P.a[0], a2, P.e[pass], tb, -tb, g_logtab[pass], pi_2, lane, bad);
+                if (pass == 0) {
+                    SQ_MARK(S, tid, 1);
+                    build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);  // :191-199
+                    SQ_MARK(S, tid, 7);
+                }
+            }
+            if (bad) S.bad[pass] = 1;
+        }
+    } else {
+        // The same schedule with a specialised copy of the code per grid (compile-time shared-memory addresses).
+        int bad = 0;
         pool_powers(S.ge, spec[0], P.e[0], g_logtab[0], pi_2, tid, nthreads);
         __syncthreads();
         pool_ratios(S.ge, spec[0], P.a[0], P.a[2], tid, nthreads);
         __syncthreads();
-        pool_place(S.ge, spec[0], tid, nthreads, bad0);
-        if (bad0) S.bad[0] = 1;
+        pool_place(S.ge, spec[0], tid, nthreads, bad);
+        if (bad) S.bad[0] = 1;
         __syncthreads();
         SQ_MARK(S, tid, 8);
-    }
-    // ---- B, C: warp 0 finishes the eta grid (fix-up walk over new nodes -- everything on the first iteration)
-    // and runs the strictly serial CDF; meanwhile all other warps do the omega grid's B0 behind a named barrier.
-    if (nwarps > 1) {
+        bad = 0;
         if (warp == 0) {
-            int bad = 0;
             pool_walk(S.ge, spec[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);  // :183-190
             SQ_MARK(S, tid, 1);
             build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);                                // :191-199
@@ -131,29 +161,15 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
             SQ_MARK(S, tid, 7);
         } else {
             const int t1 = tid - 32, n1 = nthreads - 32;
-            int bad1 = 0;
             pool_powers(S.go, spec[1], P.e[1], g_logtab[1], pi_2, t1, n1);
             asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
             pool_ratios(S.go, spec[1], P.a[0], P.a[1], t1, n1);
             asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
-            pool_place(S.go, spec[1], t1, n1, bad1);
+            pool_place(S.go, spec[1], t1, n1, bad);
             asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
-            if (warp == 1) pool_walk(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad1);  // :202-209
-            if (bad1) S.bad[1] = 1;
+            if (warp == 1) pool_walk(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad);  // :202-209
+            if (bad) S.bad[1] = 1;
         }
-    } else {  // a single warp does everything in turn
-        int bad = 0, bad1 = 0;
-        pool_walk(S.ge, spec[0], P.a[0], P.a[2], P.e[0], pi_2, -pi_2, g_logtab[0], pi_2, lane, bad);
-        build_cdf_warp(S.ge, S.cdf, __fadd_rn(P.a[0], P.a[1]), lane);
-        pool_powers(S.go, spec[1], P.e[1], g_logtab[1], pi_2, tid, nthreads);
-        __syncwarp();
-        pool_ratios(S.go, spec[1], P.a[0], P.a[1], tid, nthreads);
-        __syncwarp();
-        pool_place(S.go, spec[1], tid, nthreads, bad1);
-        __syncwarp();
-        pool_walk(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad1);
-        if (bad) S.bad[0] = 1;
-        if (bad1) S.bad[1] = 1;
     }
     __syncthreads();
     SQ_MARK(S, tid, 10);
@@ -209,32 +225,38 @@ __device__ __forceinline__ void load_M(const float *Ms, int gv, float (&M)[12])
 // phase E for one (view, slice) item: extrema over chunks [c0, c1) and, per side, the chunk that produced it
 // (-1 = no valid point improved on the +-1e6 sentinel).  The arg index is resolved later, only for the slice that
 // wins the cross-slice combine.
-template <bool kCheck>
+// kGroup = points per straight-line block (a divisor of kChunk, multiple of 4): the whole chunk when one CTA owns the SM
+// (latency regime, most ILP), 4 when several CTAs in different phases share the instruction caches.
+template <bool kCheck, int kGroup>
 __device__ __forceinline__ void scan_item(const Smem &S, const float (&M)[12], int c0, int c1,
                                           float (&best)[4], int (&cid)[4])
 {
     best[0] = 1000000.f; best[1] = -1000000.f; best[2] = 1000000.f; best[3] = -1000000.f;
     cid[0] = cid[1] = cid[2] = cid[3] = -1;
+#pragma unroll 1
     for (int c = c0; c < c1; c++) {
-        const float4 *xs = reinterpret_cast<const float4 *>(S.px + c * kChunk);
-        const float4 *ys = reinterpret_cast<const float4 *>(S.py + c * kChunk);
-        const float4 *zs = reinterpret_cast<const float4 *>(S.pz + c * kChunk);
-        float u[kChunk], w[kChunk];
-#pragma unroll
-        for (int h = 0; h < kChunk / 4; h++) {
-            float4 x = xs[h], y = ys[h], z = zs[h];
-            project_uv<kCheck>(M, x.x, y.x, z.x, u[4 * h + 0], w[4 * h + 0]);
-            project_uv<kCheck>(M, x.y, y.y, z.y, u[4 * h + 1], w[4 * h + 1]);
-            project_uv<kCheck>(M, x.z, y.z, z.z, u[4 * h + 2], w[4 * h + 2]);
-            project_uv<kCheck>(M, x.w, y.w, z.w, u[4 * h + 3], w[4 * h + 3]);
-        }
         float n0 = best[0], n1 = best[1], n2 = best[2], n3 = best[3];
+#pragma unroll 1
+        for (int g = 0; g < kChunk; g += kGroup) {
+            const float4 *xs = reinterpret_cast<const float4 *>(S.px + c * kChunk + g);
+            const float4 *ys = reinterpret_cast<const float4 *>(S.py + c * kChunk + g);
+            const float4 *zs = reinterpret_cast<const float4 *>(S.pz + c * kChunk + g);
+            float u[kGroup], w[kGroup];
 #pragma unroll
-        for (int h = 0; h < kChunk; h += 2) {
-            n0 = fmin3(n0, u[h], u[h + 1]);
-            n1 = fmax3(n1, u[h], u[h + 1]);
-            n2 = fmin3(n2, w[h], w[h + 1]);
-            n3 = fmax3(n3, w[h], w[h + 1]);
+            for (int h = 0; h < kGroup / 4; h++) {
+                float4 x = xs[h], y = ys[h], z = zs[h];
+                project_uv<kCheck>(M, x.x, y.x, z.x, u[4 * h + 0], w[4 * h + 0]);
+                project_uv<kCheck>(M, x.y, y.y, z.y, u[4 * h + 1], w[4 * h + 1]);
+                project_uv<kCheck>(M, x.z, y.z, z.z, u[4 * h + 2], w[4 * h + 2]);
+                project_uv<kCheck>(M, x.w, y.w, z.w, u[4 * h + 3], w[4 * h + 3]);
+            }
+#pragma unroll
+            for (int h = 0; h < kGroup; h += 2) {
+                n0 = fmin3(n0, u[h], u[h + 1]);
+                n1 = fmax3(n1, u[h], u[h + 1]);
+                n2 = fmin3(n2, w[h], w[h + 1]);
+                n3 = fmax3(n3, w[h], w[h + 1]);
+            }
         }
         // strict improvement only: the first chunk (lowest indices) keeps ties
         if (n0 < best[0]) { best[0] = n0; cid[0] = c; }
@@ -258,12 +280,18 @@ __device__ __forceinline__ int resolve_arg(const Smem &S, const float (&M)[12], 
     return found;
 }
 
-template <int kMaxThreads>
+// kCompact selects the small-instruction-footprint build (odam_sq_options::code_layout): same arithmetic either way.
+template <int kMaxThreads, bool kCompact>
 __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_kernel(OptArgs A)
 {
     // fixed state in static shared memory (compile-time addresses), per-launch scratch in dynamic shared memory
     __shared__ Smem S;
     extern __shared__ __align__(16) unsigned char scratch_raw[];
+#ifdef SQ_E_GROUP
+    constexpr int kGroup = SQ_E_GROUP;
+#else
+    constexpr int kGroup = kCompact ? 4 : kChunk;
+#endif
     const int tid = threadIdx.x, T = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
     // A cluster of C CTAs shares one object: every CTA runs the (cheap, deterministic) sampler redundantly and
@@ -334,7 +362,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
     __syncthreads();
 
     for (int it = 0; it < A.n_iters; it++) {
-        sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, T, it > 0);
+        sample_surface<kCompact>(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, T, it > 0);
         const bool last = it == A.n_iters - 1;
 
         // ---- E ----
@@ -346,8 +374,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_k
             int c0 = (sl * kNChunks) / slices, c1 = ((sl + 1) * kNChunks) / slices;
             float best[4];
             int cid[4];
-            if (view_all_valid(M, S.pose)) scan_item<false>(S, M, c0, c1, best, cid);
-            else scan_item<true>(S, M, c0, c1, best, cid);
+            if (view_all_valid(M, S.pose)) scan_item<false, kGroup>(S, M, c0, c1, best, cid);
+            else scan_item<true, kGroup>(S, M, c0, c1, best, cid);
             reinterpret_cast<float4 *>(ext_val)[item] = make_float4(best[0], best[1], best[2], best[3]);
             reinterpret_cast<int4 *>(ext_arg)[item] = make_int4(cid[0], cid[1], cid[2], cid[3]);
         }
@@ -567,7 +595,7 @@ __global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int
     __syncthreads();
     if (tid < 10) derive_param(S, tid);
     __syncthreads();
-    sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
+    sample_surface<true>(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
     for (int i = tid; i < kN; i += blockDim.x) {
         float *o = out_xyz + ((size_t)obj * kN + i) * 3;
         o[0] = S.px[i]; o[1] = S.py[i]; o[2] = S.pz[i];
@@ -621,7 +649,7 @@ __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, cons
     __syncthreads();
     if (tid < 10) derive_param(S, tid);
     __syncthreads();
-    sample_surface(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
+    sample_surface<true>(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
     const int v_begin = view_off[obj], V = view_off[obj + 1] - v_begin;
     for (int v = tid; v < V; v += blockDim.x) {
         float M[12];
@@ -724,6 +752,17 @@ struct DeviceState {
 static DeviceState g_dev[64];
 static std::mutex g_mu;
 
+using OptKernel = void (*)(OptArgs);
+
+// every instantiation is capped at 64 registers/thread (1024 resident threads per SM worth of registers); the compact
+// layout only exists for CTAs of up to 256 threads (it is for many small CTAs per SM)
+static OptKernel pick_kernel(int threads, int compact)
+{
+    if (compact) return threads <= 256 ? sq_optimize_kernel<256, true> : nullptr;
+    return threads <= 256 ? sq_optimize_kernel<256, false>
+                          : (threads <= 512 ? sq_optimize_kernel<512, false> : sq_optimize_kernel<1024, false>);
+}
+
 static int ensure_init(int device)
 {
     if (device < 0 || device >= 64) return ODAM_SQ_ERR_ARG;
@@ -756,9 +795,10 @@ static int ensure_init(int device)
         std::copy(one.begin(), one.end(), tab.begin() + kTabSize);
         CU(cudaMemcpyToSymbol(g_logtab, tab.data(), sizeof(double2) * 2 * kTabSize));
     }
-    CU(cudaFuncSetAttribute(sq_optimize_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
-    CU(cudaFuncSetAttribute(sq_optimize_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
-    CU(cudaFuncSetAttribute(sq_optimize_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
+    for (int compact = 0; compact < 2; compact++)
+        for (int threads : {256, 512, 1024})
+            if (auto kern = pick_kernel(threads, compact))
+                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
     CU(cudaFuncSetAttribute(sq_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaFuncSetAttribute(sq_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaFuncSetAttribute(sq_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
@@ -768,7 +808,8 @@ static int ensure_init(int device)
     return ODAM_SQ_OK;
 }
 
-struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_offset, stage_views; };
+constexpr double kCompactMaxViews = 40;  // mean views per CTA up to which the compact layout wins (measured)
+struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_offset, stage_views, compact; };
 
 // view statistics -> CTA size.  Small tracks get several point slices per view so that a CTA has >=4 warps.
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
@@ -786,12 +827,19 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     mean_views = std::max(1.0, mean_views / cluster);
     max_views = (max_views + cluster - 1) / cluster;
     int threads = opt ? opt->threads : 0;
+    // code layout: compact when several CTAs in different phases share an SM and the sampler/backward phases are a
+    // sizeable part of the iteration (few views); long tracks spend their time in the projection loop either way
+    const bool dense = n * cluster >= 2 * sm_count;
+    int layout = opt ? opt->code_layout : 0;
+    if (layout < 0 || layout > 2) return ODAM_SQ_ERR_ARG;
+    if (layout == 0) layout = (dense && mean_views <= kCompactMaxViews && (threads == 0 || threads <= 256)) ? 2 : 1;
+    if (layout == 2 && threads > 256) return ODAM_SQ_ERR_ARG;
     if (threads == 0) {
-        // measured on B200: in the throughput regime (several CTAs per SM) ~6.4 threads per view,
-        // 128..320; in the latency regime (fewer CTAs than SMs) a wide CTA with many point slices per view
+        // measured on B200: in the throughput regime (several CTAs per SM) 256 threads, 320 for
+        // long tracks; in the latency regime (fewer CTAs than SMs) a wide CTA with many point slices per view
         int v = std::max(1, (int)(mean_views + 0.5));
-        if (n * cluster >= 2 * sm_count) {
-            threads = std::min(320, std::max(128, ((int)(v * 6.4 + 31) / 32) * 32));
+        if (dense) {
+            threads = v <= 110 ? 256 : 320;
         } else {
             int s = std::max(1, std::min(max_slices, 512 / v));
             threads = std::max(64, std::min(1024, ((v * s + 31) / 32) * 32));
@@ -807,7 +855,7 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     if (stage_views) smem = stage_offset + (long)stage_views * 68;
     if (smem + (long)sizeof(Smem) > smem_optin) return ODAM_SQ_ERR_CONFIG;
     L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem; L.cluster = cluster; L.red_offset = (int)red_offset;
-    L.stage_offset = (int)stage_offset; L.stage_views = stage_views;
+    L.stage_offset = (int)stage_offset; L.stage_views = stage_views; L.compact = layout == 2;
     return ODAM_SQ_OK;
 }
 
@@ -833,8 +881,7 @@ static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L
     A.red_offset = L.red_offset;
     A.stage_offset = L.stage_offset; A.stage_views = L.stage_views;
     if (A.out_status) CU(cudaMemsetAsync(A.out_status, 0, sizeof(int32_t) * A.n, st));  // CTAs OR their flags in
-    // every instantiation is capped at 64 registers/thread (1024 resident threads per SM worth of registers)
-    void (*kern)(OptArgs) = L.threads <= 256 ? sq_optimize_kernel<256> : (L.threads <= 512 ? sq_optimize_kernel<512> : sq_optimize_kernel<1024>);
+    OptKernel kern = pick_kernel(L.threads, L.compact);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(A.n * L.cluster); cfg.blockDim = dim3(L.threads); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
@@ -894,7 +941,7 @@ const char *odam_sq_last_cuda_error(void) { return g_cuda_err; }
 int odam_sq_init(int device) { return ensure_init(device); }
 
 int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *opt, int *threads, int *smem_bytes,
-                         int *ctas_per_sm, int *cluster)
+                         int *ctas_per_sm, int *cluster, int *code_layout)
 {
     if (!view_off || n <= 0) return ODAM_SQ_ERR_ARG;
     int maxv = 0;
@@ -904,6 +951,7 @@ int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *
     if (rc) return rc;
     if (threads) *threads = L.threads;
     if (cluster) *cluster = L.cluster;
+    if (code_layout) *code_layout = L.compact ? 2 : 1;
     if (smem_bytes) *smem_bytes = L.smem;
     if (smem_bytes) *smem_bytes += (int)sizeof(Smem);
     if (ctas_per_sm) *ctas_per_sm = std::min({32, 2048 / L.threads, 65536 / (64 * L.threads), (233472 - 1024) / (L.smem + (int)sizeof(Smem) + 1024)});

@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
     from odam_b200 import _lib
     assert set(_lib.EXPORTS) == declared
-    assert lib.odam_sq_abi_version() == 1
+    assert lib.odam_sq_abi_version() == 2
     assert lib.odam_sq_error_string(-1) == b"invalid argument"
 
 
@@ -51,11 +51,16 @@ def test_argument_validation_without_gpu(lib):
     a = np.zeros(3, np.float32)
     p = a.ctypes.data_as(ctypes.c_void_p)
     assert lib.odam_sq_sample_on_batch_host(p, p, p, p, 1, 1, 999, 201, 0, 0) == -1   # only N=1000 / 201 / seed 0
-    th, sm, c, cl = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    th, sm, c, cl, lay = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     voff = np.array([0, 20, 40], np.int32)
     assert lib.odam_sq_query_launch(voff.ctypes.data_as(ctypes.c_void_p), 2, None, ctypes.byref(th), ctypes.byref(sm),
-                                    ctypes.byref(c), ctypes.byref(cl)) == 0
+                                    ctypes.byref(c), ctypes.byref(cl), ctypes.byref(lay)) == 0
     assert th.value % 32 == 0 and 32 <= th.value <= 1024 and sm.value > 0 and c.value >= 1 and cl.value in (1, 2, 4)
+    assert lay.value == 1   # two objects never share an SM: the straight-line build
+    voff = np.arange(0, 20 * 1001, 20, dtype=np.int32)   # 1000 short tracks: several CTAs per SM, compact build
+    assert lib.odam_sq_query_launch(voff.ctypes.data_as(ctypes.c_void_p), 1000, None, ctypes.byref(th), None, None,
+                                    None, ctypes.byref(lay)) == 0
+    assert lay.value == 2 and th.value == 256
 
 
 def test_no_gpu_means_loud_failure_not_fallback(lib):

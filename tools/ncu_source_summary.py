@@ -45,6 +45,9 @@ for d in data:
 for f, (i, s) in by_file.items():
     print(f"  {f}: inst {i / ti:6.2%} samples {s / ts:6.2%}")
 stall_cols = [c for c in hdr if c.startswith("stall_") and "Not Issued" not in c]
+tot = {c: sum(float(d.get(c, 0) or 0) for d in data) for c in stall_cols}
+print("stall reasons over the whole kernel: " +
+      " ".join(f"{c[6:]}={v / ts:.1%}" for c, v in sorted(tot.items(), key=lambda kv: -kv[1]) if v / ts >= 0.01))
 for d in sorted(data, key=lambda d: -d["_samp"])[:top]:
     st = sorted(((float(d.get(c, 0) or 0), c) for c in stall_cols), reverse=True)[:2]
     sts = " ".join(f"{c[6:]}={v / max(d['_samp'], 1):.0%}" for v, c in st if v > 0)

@@ -17,14 +17,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, default=2)
 ap.add_argument("--objects", type=int, default=None)
 ap.add_argument("--iters", type=int, default=None)
+ap.add_argument("--views", type=int, default=None)
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--max-slices", type=int, default=0)
 ap.add_argument("--launches", type=int, default=2)
 ap.add_argument("--cycles", action="store_true")
 ap.add_argument("--cluster", type=int, default=0)
+ap.add_argument("--layout", type=int, default=0, help="odam_sq_options.code_layout: 0 auto, 1 straight-line, 2 compact")
 a = ap.parse_args()
 c = synthetic.CONFIGS[a.config]
-scene = synthetic.make_scene(a.objects or c["n_objects"], c["n_views"], seed=a.config, device="cuda:0")
+scene = synthetic.make_scene(a.objects or c["n_objects"], a.views or c["n_views"], seed=a.config, device="cuda:0")
 tracks = api.pack_scene(scene)
 dt = api.DeviceTracks(tracks, "cuda:0", api.prior_table() if c["prior"] else None)
 iters = a.iters or c["n_iters"]
@@ -32,7 +34,7 @@ out = None
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.launches + 1)]
 ev[0].record()
 for k in range(a.launches):
-    out = api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cluster=a.cluster)
+    out = api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cluster=a.cluster, code_layout=a.layout)
     ev[k + 1].record()
 torch.cuda.synchronize()
 units = float(tracks.total_views) * iters
@@ -43,7 +45,7 @@ for k in range(a.launches):
 print("flagged", int((out["status"].cpu() & 3 != 0).sum()))
 if a.cycles:
     cyc = torch.zeros((tracks.n, 12), dtype=torch.int64, device="cuda:0")
-    api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc, cluster=a.cluster)
+    api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc, cluster=a.cluster, code_layout=a.layout)
     torch.cuda.synchronize()
     c = cyc.cpu().numpy().astype(float) / iters
     names = ["-", "B fix-up walk (eta)", "D points", "E project", "F backward + warp reduce", "-", "G reduce (+cluster), Adam, derive", "C cdf",
