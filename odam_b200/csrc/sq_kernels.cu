@@ -280,9 +280,13 @@ __device__ __forceinline__ int resolve_arg(const Smem &S, const float (&M)[12], 
     return found;
 }
 
+#ifndef SQ_COMPACT_BLOCKS
+#define SQ_COMPACT_BLOCKS 4
+#endif
+#define SQ_MIN_BLOCKS(threads, compact) ((compact) ? SQ_COMPACT_BLOCKS : 1024 / (threads))
 // kCompact selects the small-instruction-footprint build (odam_sq_options::code_layout): same arithmetic either way.
 template <int kMaxThreads, bool kCompact>
-__global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) sq_optimize_kernel(OptArgs A)
+__global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompact)) sq_optimize_kernel(OptArgs A)
 {
     // fixed state in static shared memory (compile-time addresses), per-launch scratch in dynamic shared memory
     __shared__ Smem S;
