@@ -70,7 +70,7 @@ extern "C" {
 
 /* Optional knobs and test-only inputs/outputs; zero-initialise, then set what you need. */
 typedef struct odam_sq_options {
-    int threads;            /* CTA size (multiple of 32, 32..1024); 0 = choose from the view counts   */
+    int threads;            /* CTA size (multiple of 32, 64..1024); 0 = choose from the view counts   */
     int max_slices;         /* max point-slices per view (1..25); 0 = default                          */
     int cluster;            /* CTAs per object (thread-block cluster, views tiled across them): 1, 2 or 4; 0 = auto
                                (2 or 4 when there are fewer objects than SMs)                                 */

@@ -849,7 +849,7 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
             threads = std::max(64, std::min(1024, ((v * s + 31) / 32) * 32));
         }
     }
-    if (threads % 32 || threads < 32 || threads > 1024) return ODAM_SQ_ERR_ARG;
+    if (threads % 32 || threads < 64 || threads > 1024) return ODAM_SQ_ERR_ARG;  // two warps share the sampler's tail
     long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
     long red_offset = std::max<long>(items * 4 * 8, (long)kSpecBytes);  // phase-E results alias the B0 scratch
     long smem = red_offset + (threads / 32) * (kRed + 3) * 4;            // + cross-warp reduction rows
