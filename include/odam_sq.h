@@ -143,9 +143,14 @@ int odam_sq_sample_on_batch_host(const float *shapes, const float *epsilons, flo
  * in TFLOP/s counting an FMA as 2 flop.  Best of 4 timed launches after one warm-up. */
 int odam_sq_fma_peak(int device, double *tflops);
 
+/* Device self-test: the kernels' split IEEE-754 division (one refined reciprocal shared by several quotients) against
+ * the compiler's __fdiv_rn on n random operand pairs; *mismatches must come back 0. */
+int odam_sq_selftest(int device, uint32_t seed, long long n, long long *mismatches);
+
 /* The launch configuration odam_sq_optimize would use (for benchmarks/logging). */
 int odam_sq_query_launch(const int32_t *view_off_host, int n, const odam_sq_options *opt,
-                         int *threads, int *smem_bytes, int *ctas_per_sm, int *cluster, int *code_layout);
+                         int *threads, int *smem_bytes, int *ctas_per_sm, int *cluster, int *code_layout,
+                         int *max_slices);
 
 #ifdef __cplusplus
 }

@@ -114,10 +114,11 @@ def query_launch(view_off, threads=0, max_slices=0, cluster=0, code_layout=0):
     view_off = np.ascontiguousarray(view_off, np.int32)
     o = _lib.Options()
     o.threads, o.max_slices, o.cluster, o.code_layout = int(threads), int(max_slices), int(cluster), int(code_layout)
-    th, sm, cps, cl, lay = (C.c_int() for _ in range(5))
+    th, sm, cps, cl, lay, ms = (C.c_int() for _ in range(6))
     _lib.check(L.odam_sq_query_launch(_lib.ptr(view_off), len(view_off) - 1, C.byref(o), C.byref(th), C.byref(sm),
-                                      C.byref(cps), C.byref(cl), C.byref(lay)))
-    return dict(threads=th.value, smem_bytes=sm.value, ctas_per_sm=cps.value, cluster=cl.value, code_layout=lay.value)
+                                      C.byref(cps), C.byref(cl), C.byref(lay), C.byref(ms)))
+    return dict(threads=th.value, smem_bytes=sm.value, ctas_per_sm=cps.value, cluster=cl.value, code_layout=lay.value,
+                max_slices=ms.value)
 
 
 def _options(n, SV, n_iters, threads, max_slices, m0, v0, step0, s0, extras, alloc, cluster=0, code_layout=0):
@@ -239,7 +240,7 @@ def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr
     if threads == 0 or cluster == 0 or code_layout == 0:
         # choose on the host from the host copy of view_off (avoids the library's D2H read-back)
         q = query_launch(dt.view_off_host, threads, max_slices, cluster, code_layout)
-        threads, cluster, code_layout = q["threads"], q["cluster"], q["code_layout"]
+        threads, cluster, code_layout, max_slices = q["threads"], q["cluster"], q["code_layout"], q["max_slices"]
     o.threads, o.max_slices, o.cluster, o.code_layout = int(threads), int(max_slices), int(cluster), int(code_layout)
     o.max_views = int(np.diff(dt.view_off_host).max()) if dt.n else 0
     if cycles is not None:  # int64 CUDA tensor [n, 8]: per-phase SM cycles (diagnostics)

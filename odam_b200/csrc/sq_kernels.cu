@@ -509,55 +509,68 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
             }
         }
         __syncthreads();
-        // ---- G: gradient of parameter k = tid (+ prior), Adam, derived quantities for the next iteration; the loss
-        // on lane 9.  (torch/optim/adam.py _single_tensor_adam; roundings as probed against torch's CPU kernels)
-        if (tid < 9) {
-            float g = red[0][tid];
-            if (A.prior && tid >= 4 && tid < 7) {  // d/ds of 20 (s0-s)^T A (s0-s)  (sq_libs.py:463-466)
-                const int r = tid - 4;
-                float sym = 0.f;
-                for (int cc = 0; cc < 3; cc++)
-                    sym = __fmaf_rn(S.prior[3 * r + cc] + S.prior[3 * cc + r], S.s0[cc] - S.par[4 + cc], sym);
-                g += -20.f * sym;
-            }
-            if (tid >= 7 && !A.optimize_shapes) g = 0.f;
-            S.grad[tid] = g;
-            if (!isfinite(g)) atomicOr(&S.status, ODAM_SQ_ST_NONFINITE);
-        }
-        if (tid == 9) {
-            // loss = sum over sides of mean over ALL views (sq_libs.py:428-429) + prior (:463-466)
-            float loss = 0.f;
-            for (int sd2 = 0; sd2 < 4; sd2++) loss = __fadd_rn(loss, __fdiv_rn(red[0][9 + sd2], (float)Vall));
-            if (A.prior) {
-                float dd[3] = {S.s0[0] - S.par[4], S.s0[1] - S.par[5], S.s0[2] - S.par[6]};
-                float q3 = 0.f;
-                for (int r = 0; r < 3; r++) {
-                    float row = 0.f;
-                    for (int cc = 0; cc < 3; cc++) row = __fmaf_rn(S.prior[3 * r + cc], dd[cc], row);
-                    q3 = __fmaf_rn(dd[r], row, q3);
+        // ---- G: gradient (+ prior), Adam (torch/optim/adam.py _single_tensor_adam; roundings as probed against torch's
+        // CPU kernels) and the derived quantities for the next iteration, one lane per parameter; the loss on one more
+        // lane.  The divergent code paths (prior, loss, sin/cos of the yaw, sigmoid of the shapes) sit on different
+        // warps so that they run side by side instead of one after the other: lane index = parameter index in every
+        // warp, so that warps may double up when the CTA has fewer than four.
+        {
+            int k = -1;
+            if (warp == 0 && lane < 7 && lane != 3) k = lane;       // translation, scales (+ prior)
+            if (warp == 3 % nwarps && lane == 3) k = 3;             // yaw -> sin, cos
+            if (warp == 2 % nwarps && (lane == 7 || lane == 8)) k = lane;  // shapes -> sigmoid
+            const bool loss_lane = warp == 1 && lane == 9;
+            if (k >= 0) {
+                float g = red[0][k];
+                if (A.prior && k >= 4 && k < 7) {  // d/ds of 20 (s0-s)^T A (s0-s)  (sq_libs.py:463-466)
+                    const int r = k - 4;
+                    float sym = 0.f;
+                    for (int cc = 0; cc < 3; cc++)
+                        sym = __fmaf_rn(S.prior[3 * r + cc] + S.prior[3 * cc + r], S.s0[cc] - S.par[4 + cc], sym);
+                    g += -20.f * sym;
                 }
-                loss = __fadd_rn(loss, __fmul_rn(q3, 20.f));
+                if (k >= 7 && !A.optimize_shapes) g = 0.f;
+                S.grad[k] = g;
+                if (!isfinite(g)) atomicOr(&S.status, ODAM_SQ_ST_NONFINITE);
             }
-            if (crank == 0) A.out_loss[(size_t)obj * A.n_iters + it] = loss;
-            if (!isfinite(loss)) atomicOr(&S.status, ODAM_SQ_ST_NONFINITE);
-            if (S.bad[0] | S.bad[1]) atomicOr(&S.status, ODAM_SQ_ST_SAMPLER);
+            float dd[3] = {0.f, 0.f, 0.f};
+            if (loss_lane) { dd[0] = S.s0[0] - S.par[4]; dd[1] = S.s0[1] - S.par[5]; dd[2] = S.s0[2] - S.par[6]; }
+            // warps 0 and 1: every read of the scales of this iteration comes before their update
+            if (warp < 2) asm volatile("bar.sync 2, 64;" ::: "memory");
+            if (loss_lane) {
+                // loss = sum over sides of mean over ALL views (sq_libs.py:428-429) + prior (:463-466)
+                float loss = 0.f;
+                for (int sd2 = 0; sd2 < 4; sd2++) loss = __fadd_rn(loss, __fdiv_rn(red[0][9 + sd2], (float)Vall));
+                if (A.prior) {
+                    float q3 = 0.f;
+                    for (int r = 0; r < 3; r++) {
+                        float row = 0.f;
+                        for (int cc = 0; cc < 3; cc++) row = __fmaf_rn(S.prior[3 * r + cc], dd[cc], row);
+                        q3 = __fmaf_rn(dd[r], row, q3);
+                    }
+                    loss = __fadd_rn(loss, __fmul_rn(q3, 20.f));
+                }
+                if (crank == 0) A.out_loss[(size_t)obj * A.n_iters + it] = loss;
+                if (!isfinite(loss)) atomicOr(&S.status, ODAM_SQ_ST_NONFINITE);
+                if (S.bad[0] | S.bad[1]) atomicOr(&S.status, ODAM_SQ_ST_SAMPLER);
+                derive_param(S, 9);  // per-iteration resets of the sampler state
+            }
+            if (k >= 0) {
+                if (k < 7 || A.optimize_shapes) {
+                    float g = S.grad[k], m = S.m[k], v = S.v[k], p = S.par[k];
+                    float alpha = A.adam_tab[it * 4 + (k < 7 ? 0 : 1)];
+                    float bc2s = A.adam_tab[it * 4 + 2];
+                    m = __fmaf_rn(A.beta1w, __fsub_rn(g, m), m);
+                    v = __fmul_rn(v, A.beta2);
+                    v = __fmaf_rn(__fmul_rn(A.beta2w, g), g, v);
+                    float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), A.eps);
+                    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(alpha, m), denom));
+                    S.m[k] = m; S.v[k] = v; S.par[k] = p;
+                }
+                if (A.out_param_hist && crank == 0) A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + k] = S.par[k];
+                derive_param(S, k);
+            }
         }
-        __syncwarp();  // lanes 4..6 and 9 read the scales before lanes 4..6 update them
-        if (tid < (A.optimize_shapes ? 9 : 7)) {
-            float g = S.grad[tid], m = S.m[tid], v = S.v[tid], p = S.par[tid];
-            float alpha = A.adam_tab[it * 4 + (tid < 7 ? 0 : 1)];
-            float bc2s = A.adam_tab[it * 4 + 2];
-            m = __fmaf_rn(A.beta1w, __fsub_rn(g, m), m);
-            v = __fmul_rn(v, A.beta2);
-            v = __fmaf_rn(__fmul_rn(A.beta2w, g), g, v);
-            float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2s), A.eps);
-            p = __fadd_rn(p, __fdiv_rn(__fmul_rn(alpha, m), denom));
-            S.m[tid] = m; S.v[tid] = v; S.par[tid] = p;
-            if (A.out_param_hist && crank == 0) A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = p;
-        }
-        if (tid < 10) derive_param(S, tid);
-        if (A.out_param_hist && crank == 0 && tid >= 7 && tid < 9 && !A.optimize_shapes)
-            A.out_param_hist[((size_t)obj * A.n_iters + it) * 9 + tid] = S.par[tid];
         if (last && crank == 0) {
             if (A.out_eta_idx) for (int i = tid; i < kN; i += T) A.out_eta_idx[(size_t)obj * kN + i] = S.pj[i];
             if (A.out_grids) for (int i = tid; i < kG; i += T) {
@@ -673,6 +686,25 @@ __global__ void __launch_bounds__(256) sq_boxes_kernel(const float *params, cons
 }
 
 // FP32 FMA-pipe roofline probe: 8 independent FFMA chains per thread, no memory traffic.
+// self-test of the split IEEE division (sq_device.cuh: div_rn_recip / div_rn_by) against __fdiv_rn on random operands
+// covering the whole range div_rn_safe() admits; every 4th pair shares its divisor's neighbourhood in the last place
+__global__ void div_selftest_kernel(uint32_t seed, long long n, unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint64_t x = (uint64_t)i * 0x9E3779B97F4A7C15ull + seed;   // splitmix64
+        x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+        uint32_t ma = (uint32_t)x & 0x7fffffu, mb = (uint32_t)(x >> 23) & 0x7fffffu;
+        uint32_t ea = 67u + (uint32_t)((x >> 46) % 121u), eb = 67u + (uint32_t)((x >> 54) % 121u);   // 2^-60 .. 2^60
+        if ((i & 3) == 3) { mb = ma ^ ((uint32_t)(x >> 60) & 7u); eb = ea; }        // quotients next to 1
+        const float a = __uint_as_float((ea << 23) | ma), b = __uint_as_float((eb << 23) | mb);
+        const float sa = (x >> 63) ? -a : a;
+        if (!(div_rn_safe(sa) && div_rn_safe(b))) { bad++; continue; }
+        if (__float_as_uint(div_rn_by(sa, b, div_rn_recip(b))) != __float_as_uint(__fdiv_rn(sa, b))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 __global__ void __launch_bounds__(1024) fma_peak_kernel(float *sink, int iters, float a, float b)
 {
     float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
@@ -819,7 +851,8 @@ struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_off
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
                          int smem_optin, LaunchCfg &L)
 {
-    int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= sm_count ? 8 : 25);
+    // point slices per view: many for a lone CTA (latency), 8 when CTAs share SMs (16 for very short tracks)
+    int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= sm_count ? (mean_views < 12 ? 16 : 8) : 25);
     if (max_slices < 1 || max_slices > 25) return ODAM_SQ_ERR_ARG;
     // view-tiled clusters: when there are fewer objects than SMs, 2 or 4 CTAs (on different SMs) share an object;
     // long tracks (>= 128 views) are split in two in any case (finer load balance across SMs)
@@ -945,7 +978,7 @@ const char *odam_sq_last_cuda_error(void) { return g_cuda_err; }
 int odam_sq_init(int device) { return ensure_init(device); }
 
 int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *opt, int *threads, int *smem_bytes,
-                         int *ctas_per_sm, int *cluster, int *code_layout)
+                         int *ctas_per_sm, int *cluster, int *code_layout, int *max_slices)
 {
     if (!view_off || n <= 0) return ODAM_SQ_ERR_ARG;
     int maxv = 0;
@@ -956,6 +989,7 @@ int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *
     if (threads) *threads = L.threads;
     if (cluster) *cluster = L.cluster;
     if (code_layout) *code_layout = L.compact ? 2 : 1;
+    if (max_slices) *max_slices = L.max_slices;
     if (smem_bytes) *smem_bytes = L.smem;
     if (smem_bytes) *smem_bytes += (int)sizeof(Smem);
     if (ctas_per_sm) *ctas_per_sm = std::min({32, 2048 / L.threads, 65536 / (64 * L.threads), (233472 - 1024) / (L.smem + (int)sizeof(Smem) + 1024)});
@@ -1293,6 +1327,27 @@ int odam_sq_fma_peak(int device, double *tflops)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *tflops = best;
+    CU(cudaSetDevice(cur));
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_selftest(int device, uint32_t seed, long long n, long long *mismatches)
+{
+    if (!mismatches || n < 0) return ODAM_SQ_ERR_ARG;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    CU(cudaSetDevice(device));
+    { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, 4096); }
+    if (rc) { cudaSetDevice(cur); return rc; }
+    CU(cudaMemsetAsync(D.dbuf, 0, 8, D.stream));
+    div_selftest_kernel<<<D.sm_count * 4, 256, 0, D.stream>>>(seed, n, (unsigned long long *)D.dbuf);
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, D.dbuf, 8, cudaMemcpyDeviceToHost, D.stream));
+    CU(cudaStreamSynchronize(D.stream));
+    *mismatches = (long long)h;
     CU(cudaSetDevice(cur));
     return ODAM_SQ_OK;
 }

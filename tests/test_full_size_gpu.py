@@ -32,13 +32,12 @@ def _check(api, coracle, cfg_idx, n_objects=None, n_iters=None, sample=8, oracle
     # the launch configuration (CTA size, slices, cluster) is chosen from the batch statistics; replay the picked objects
     # with the SAME configuration so that only the batch composition differs
     cfg = api.query_launch(tracks.view_off)
-    max_slices = 8 if tracks.n >= 148 else 25
     n_param_ok = 0
     for i in pick:
         # ... except the code layout on every other pick: the two builds of the kernel must agree bit for bit
         layout = cfg["code_layout"] if (i % 2 == 0 or cfg["threads"] > 256) else 3 - cfg["code_layout"]
         one = api.optimize_host(tracks.slice(i, i + 1), prior=prior, n_iters=n_iters, threads=cfg["threads"],
-                                max_slices=max_slices, cluster=cfg["cluster"], code_layout=layout)
+                                max_slices=cfg["max_slices"], cluster=cfg["cluster"], code_layout=layout)
         assert np.array_equal(one["params"][0], P[i]) and np.array_equal(one["loss"][0], L[i]), i
         a, b = tracks.view_off[i], tracks.view_off[i + 1]
         r = coracle.run(tracks.init[i], tracks.Ms[a:b], tracks.box[a:b], tracks.mask[a:b],
