@@ -48,9 +48,11 @@ struct alignas(16) Smem {
     long long tmark, cyc[12];                // per-phase clock64() accumulation by thread 0 (diagnostics)
 };
 
+// only when the caller asked for the per-phase cycle counts (`prof` in scope): the clock read and the shared-memory
+// round trip sit on thread 0's critical path otherwise
 #define SQ_MARK(S, tid, k)                                                \
     do {                                                                   \
-        if ((tid) == 0) {                                                  \
+        if (prof && (tid) == 0) {                                          \
             long long now_ = clock64();                                    \
             (S).cyc[k] += now_ - (S).tmark;                                \
             (S).tmark = now_;                                              \
@@ -102,7 +104,8 @@ __device__ __forceinline__ void derive_param(Smem &S, int k)
 // phases B-D: derived quantities in S.pose -> 1000 world points in S.px/py/pz (+ S.pj, grids)
 // kCompact: both grids through one copy of the B0/walk code (see the loop below); otherwise one specialised copy each.
 template <bool kCompact>
-__device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid, int nthreads, bool have_prev)
+__device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid, int nthreads, bool have_prev,
+                                               bool prof = false)
 {
     const int warp = tid >> 5, lane = tid & 31;
     // ---- B0: node pool of the previous tree -> powers, split ratios, slots; B: fix-up walk; C: CDF ----
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
 #endif
     const int tid = threadIdx.x, T = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+    const bool prof = A.out_cycles != nullptr;
     // A cluster of C CTAs shares one object: every CTA runs the (cheap, deterministic) sampler redundantly and
     // projects its own tile of the views; the 13 partial sums meet through distributed shared memory once per iteration.
     const int C = A.cluster;
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
     __syncthreads();
 
     for (int it = 0; it < A.n_iters; it++) {
-        sample_surface<kCompact>(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, T, it > 0);
+        sample_surface<kCompact>(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, T, it > 0, prof);
         const bool last = it == A.n_iters - 1;
 
         // ---- E ----
