@@ -94,7 +94,7 @@ typedef struct odam_sq_options {
     uint8_t *out_eta_idx;   /* [n][1000] eta-grid index of every sample, LAST iteration                */
     float *out_grids;       /* [n][2][201] eta grid then omega grid, LAST iteration                    */
     float *out_param_hist;  /* [n][n_iters][9] parameters after every step                             */
-    int64_t *out_cycles;    /* device-pointer entry only: [n][12] SM cycles per phase as seen by thread 0, summed over iterations
+    int64_t *out_cycles;    /* device-pointer entry only: [n][16] SM cycles per phase as seen by thread 0, summed over iterations
                                (see tools/prof_run.py for the slot names) */
 } odam_sq_options;
 

@@ -45,7 +45,8 @@ struct alignas(16) Smem {
     Pose pose;
     int status;
     int bad[2];
-    long long tmark, cyc[12];                // per-phase clock64() accumulation by thread 0 (diagnostics)
+    float adam_now[4];                       // this iteration's row of the Adam table (fetched early)
+    long long tmark, cyc[16];                // per-phase clock64() accumulation by thread 0 (diagnostics)
 };
 
 // only when the caller asked for the per-phase cycle counts (`prof` in scope): the clock read and the shared-memory
@@ -269,16 +270,33 @@ __device__ __forceinline__ void scan_item(const Smem &S, const float (&M)[12], i
     }
 }
 
-// first point of chunk `c` whose projection (the bit-identical project_uv) equals the extremum `best`
-__device__ __forceinline__ int resolve_arg(const Smem &S, const float (&M)[12], int c, bool y_side, float best)
+// two rows of a camera matrix: `row` (0 = x, 1 = y) and the z row
+template <bool kStaged>
+__device__ __forceinline__ void load_M2(const float *Ms, int gv, int row, float (&Mr)[4], float (&Mz)[4])
+{
+    const float4 *p = reinterpret_cast<const float4 *>(Ms + (size_t)gv * 12);
+    float4 r, z;
+    if (kStaged) { r = p[row]; z = p[2]; }
+    else { r = __ldg(p + row); z = __ldg(p + 2); }
+    Mr[0] = r.x; Mr[1] = r.y; Mr[2] = r.z; Mr[3] = r.w;
+    Mz[0] = z.x; Mz[1] = z.y; Mz[2] = z.z; Mz[3] = z.w;
+}
+
+// first point of chunk `c` whose projected coordinate (the same operations as project_uv<true>, for the one image
+// axis this side lives on) equals the extremum `best`
+__device__ __forceinline__ int resolve_arg(const Smem &S, const float (&Mr)[4], const float (&Mz)[4], int c, float best)
 {
     int found = -1;
     const int base = c * kChunk;
+    const float mz3 = __fadd_rn(Mz[3], 1e-6f);  // as in the scan
 #pragma unroll 4
     for (int h = kChunk - 1; h >= 0; h--) {
-        float u, w;
-        project_uv<true>(M, S.px[base + h], S.py[base + h], S.pz[base + h], u, w);
-        if ((y_side ? w : u) == best) found = base + h;
+        const float X = S.px[base + h], Y = S.py[base + h], Z = S.pz[base + h];
+        const float q = __fmaf_rn(X, Mr[0], __fmaf_rn(Y, Mr[1], __fmaf_rn(Z, Mr[2], Mr[3])));
+        const float qz = __fmaf_rn(X, Mz[0], __fmaf_rn(Y, Mz[1], __fmaf_rn(Z, Mz[2], mz3)));
+        float r = rcp_approx(qz);
+        r = qz > 0.500001f ? r : __int_as_float(0x7fc00000);
+        if (__fmul_rn(q, r) == best) found = base + h;
     }
     return found;
 }
@@ -287,6 +305,13 @@ __device__ __forceinline__ int resolve_arg(const Smem &S, const float (&M)[12], 
 #define SQ_COMPACT_BLOCKS 4
 #endif
 #define SQ_MIN_BLOCKS(threads, compact) ((compact) ? SQ_COMPACT_BLOCKS : 1024 / (threads))
+// phase-E work item -> view << 16 | first chunk << 8 | end chunk: item = slice * V + view, the 63 chunks split evenly
+__device__ __forceinline__ unsigned item_code(int item, int V, int slices)
+{
+    const int sl = item / V, v = item - sl * V;
+    return ((unsigned)v << 16) | (unsigned)(((sl * kNChunks) / slices) << 8) | (unsigned)(((sl + 1) * kNChunks) / slices);
+}
+
 // kCompact selects the small-instruction-footprint build (odam_sq_options::code_layout): same arithmetic either way.
 template <int kMaxThreads, bool kCompact>
 __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompact)) sq_optimize_kernel(OptArgs A)
@@ -310,15 +335,15 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
     const int Vall = A.view_off[obj + 1] - v_obj;
     const int v_begin = v_obj + (Vall * crank) / C;
     const int V = v_obj + (Vall * (crank + 1)) / C - v_begin;   // this CTA's views
-    // per-item results live after the fixed part of shared memory
-    float *ext_val = reinterpret_cast<float *>(scratch_raw);
+    // per-(item, side) results of phase E live after the fixed part of shared memory: {key, chunk id} where key is the
+    // extremum for the min sides and MINUS the extremum for the max sides, so that phase F combines slices with "<" only
+    float2 *ext = reinterpret_cast<float2 *>(scratch_raw);
     // cross-warp reduction scratch sits behind the per-item area (its size depends on the CTA size, not on 32 warps)
     float(*red)[kRed + 3] = reinterpret_cast<float(*)[kRed + 3]>(scratch_raw + A.red_offset);
 
     int slices = V > 0 ? T / V : 1;
     slices = max(1, min(slices, A.max_slices));
     const int n_items = V * slices;
-    int *ext_arg = reinterpret_cast<int *>(ext_val + 4 * n_items);
 
     if (tid < 9) {
         S.par[tid] = A.init[(size_t)obj * 9 + tid];
@@ -329,7 +354,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
     if (tid < 3) S.s0[tid] = A.s0 ? A.s0[(size_t)obj * 3 + tid] : A.init[(size_t)obj * 9 + 4 + tid];
     if (tid == 0) {
         S.status = 0;
-        for (int k = 0; k < 12; k++) S.cyc[k] = 0;
+        for (int k = 0; k < 16; k++) S.cyc[k] = 0;
         S.tmark = clock64();
         const float pi = 3.14159274101257324f, pi_2 = __fmul_rn(pi, 0.5f);
         pool_init(S.ge, pi_2, -pi_2);
@@ -365,27 +390,31 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
     const float *Bsrc = staged ? sBox : A.box + (size_t)v_begin * 4;
     const uint8_t *Ksrc = staged ? sMask : A.mask + (size_t)v_begin * 4;
 
+    const unsigned my_item = tid < n_items ? item_code(tid, V, slices) : 0u;
     const float invV = Vall > 0 ? __fdiv_rn(1.f, (float)Vall) : 0.f;
     if (tid < 10) derive_param(S, tid);
     __syncthreads();
 
     for (int it = 0; it < A.n_iters; it++) {
+        // this iteration's Adam step sizes, fetched now: the load is off the critical path by the time phase G wants them
+        if (tid < 3) S.adam_now[tid] = A.adam_tab[it * 4 + tid];
         sample_surface<kCompact>(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, T, it > 0, prof);
         const bool last = it == A.n_iters - 1;
 
         // ---- E ----
         for (int item = tid; item < n_items; item += T) {
-            int sl = item / V, v = item - sl * V;
+            unsigned code = my_item;   // this thread's first item was decoded once, before the first iteration
+            if (item != tid) code = item_code(item, V, slices);
+            const int v = code >> 16, c0 = (code >> 8) & 0xff, c1 = code & 0xff;
             float M[12];
             if (staged) load_M<true>(Msrc, v, M); else load_M<false>(Msrc, v, M);
             M[11] = __fadd_rn(M[11], 1e-6f);  // the reference's |z| + 1e-6, folded (see project_uv)
-            int c0 = (sl * kNChunks) / slices, c1 = ((sl + 1) * kNChunks) / slices;
             float best[4];
             int cid[4];
             if (view_all_valid(M, S.pose)) scan_item<false, kGroup>(S, M, c0, c1, best, cid);
             else scan_item<true, kGroup>(S, M, c0, c1, best, cid);
-            reinterpret_cast<float4 *>(ext_val)[item] = make_float4(best[0], best[1], best[2], best[3]);
-            reinterpret_cast<int4 *>(ext_arg)[item] = make_int4(cid[0], cid[1], cid[2], cid[3]);
+            reinterpret_cast<float4 *>(ext)[2 * item] = make_float4(best[0], __int_as_float(cid[0]), -best[1], __int_as_float(cid[1]));
+            reinterpret_cast<float4 *>(ext)[2 * item + 1] = make_float4(best[2], __int_as_float(cid[2]), -best[3], __int_as_float(cid[3]));
         }
         __syncthreads();
         SQ_MARK(S, tid, 3);
@@ -400,40 +429,39 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
         for (int pr = tid; pr < 4 * V; pr += T) {
             int v = pr >> 2;
             // combine slices in index order; strict comparison keeps the first index on ties
-            float best = ext_val[v * 4 + sd];
-            int cid = ext_arg[v * 4 + sd];
+            float2 rec = ext[pr];
 #pragma unroll 4
             for (int sl = 1; sl < slices; sl++) {   // branch-free so that the loads of several slices are in flight
-                const float b = ext_val[(sl * V + v) * 4 + sd];
-                const int cb = ext_arg[(sl * V + v) * 4 + sd];
-                const bool better = (sd & 1) ? (b > best) : (b < best);
-                best = better ? b : best;
-                cid = better ? cb : cid;
+                const float2 b = ext[sl * 4 * V + pr];
+                const bool better = b.x < rec.x;
+                rec.x = better ? b.x : rec.x;
+                rec.y = better ? b.y : rec.y;
             }
+            float best = (sd & 1) ? -rec.x : rec.x;
+            const int cid = __float_as_int(rec.y);
+            SQ_MARK(S, tid, 0);
             int gv = v_begin + v;
             float target = Bsrc[v * 4 + sd];
             float mk = Ksrc[v * 4 + sd] ? 1.f : 0.f;
+            // Only two rows of the camera matrix matter to this side: Mr = the x row (sides 0,1) or the y row (2,3), Mz.
             // The scan ranks points with a 1-ulp reciprocal; the winner's coordinate is now re-evaluated with the
             // reference's own rounding sequence (k-ordered FMA chain of the CPU GEMM, IEEE division) so that the
             // loss carries the same fp32 noise as the reference's instead of an independent sample of it.
-            float M[12];
-            float qx = 0.f, qy = 0.f, qz = 1.f, d = 1.f;
+            float Mr[4], Mz[4];
+            float num = 0.f, qz = 1.f, d = 1.f;
             int arg = -1;
             if (cid >= 0) {
-                if (staged) load_M<true>(Msrc, v, M); else load_M<false>(Msrc, v, M);
-                const float m11 = M[11];
-                M[11] = __fadd_rn(m11, 1e-6f);
-                arg = resolve_arg(S, M, cid, sd >= 2, best);
-                M[11] = m11;
+                if (staged) load_M2<true>(Msrc, v, sd >> 1, Mr, Mz); else load_M2<false>(Msrc, v, sd >> 1, Mr, Mz);
+                arg = resolve_arg(S, Mr, Mz, cid, best);
             }
             if (arg >= 0) {
                 float X = S.px[arg], Y = S.py[arg], Z = S.pz[arg];
-                qx = __fadd_rn(__fmaf_rn(Z, M[2], __fmaf_rn(Y, M[1], __fmul_rn(X, M[0]))), M[3]);
-                qy = __fadd_rn(__fmaf_rn(Z, M[6], __fmaf_rn(Y, M[5], __fmul_rn(X, M[4]))), M[7]);
-                qz = __fadd_rn(__fmaf_rn(Z, M[10], __fmaf_rn(Y, M[9], __fmul_rn(X, M[8]))), M[11]);
+                num = __fadd_rn(__fmaf_rn(Z, Mr[2], __fmaf_rn(Y, Mr[1], __fmul_rn(X, Mr[0]))), Mr[3]);
+                qz = __fadd_rn(__fmaf_rn(Z, Mz[2], __fmaf_rn(Y, Mz[1], __fmul_rn(X, Mz[0]))), Mz[3]);
                 d = __fadd_rn(fabsf(qz), 1e-6f);
-                best = __fdiv_rn(sd < 2 ? qx : qy, d);
+                best = __fdiv_rn(num, d);
             }
+            SQ_MARK(S, tid, 5);
             float diff = __fsub_rn(best, target);
             float l = fabsf(diff);
             if (!(l == l)) l = 0.f;  // sq_libs.py:426-427
@@ -446,12 +474,11 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
             if (arg < 0 || mk == 0.f || !(diff == diff)) continue;
             // gradient through the arg-extreme point
             float c = __fmul_rn(__fmul_rn(sgnf(diff), mk), invV);
-            float num = sd < 2 ? qx : qy;
             float g_lin = __fdiv_rn(c, d);                                        // d(u)/d(q_x or q_y)
             float g_z = -__fmul_rn(__fdiv_rn(__fmul_rn(c, num), __fmul_rn(d, d)), sgnf(qz));  // d(u)/d(q_z)
-            float gp0 = __fmaf_rn(M[8], g_z, __fmul_rn(sd < 2 ? M[0] : M[4], g_lin));
-            float gp1 = __fmaf_rn(M[9], g_z, __fmul_rn(sd < 2 ? M[1] : M[5], g_lin));
-            float gp2 = __fmaf_rn(M[10], g_z, __fmul_rn(sd < 2 ? M[2] : M[6], g_lin));
+            float gp0 = __fmaf_rn(Mz[0], g_z, __fmul_rn(Mr[0], g_lin));
+            float gp1 = __fmaf_rn(Mz[1], g_z, __fmul_rn(Mr[1], g_lin));
+            float gp2 = __fmaf_rn(Mz[2], g_z, __fmul_rn(Mr[2], g_lin));
             int j = S.pj[arg], k = g_k_omega[arg];
             const float4 se = S.ge.slot[j], so = S.go.slot[k];
             float x0, y0, z0;
@@ -476,6 +503,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
                 acc[8] += ge2 * 1.4f * P.sig[1] * (1.f - P.sig[1]);
             }
         }
+        SQ_MARK(S, tid, 9);
         // ---- G: deterministic reduction (butterfly inside the warp, warp order across) ----
 #pragma unroll
         for (int k = 0; k < 4; k++) acc[9 + k] = sd == k ? lside : 0.f;
@@ -512,7 +540,9 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
                 red[0][tid] = x;
             }
         }
+        SQ_MARK(S, tid, 12);
         __syncthreads();
+        SQ_MARK(S, tid, 13);
         // ---- G: gradient (+ prior), Adam (torch/optim/adam.py _single_tensor_adam; roundings as probed against torch's
         // CPU kernels) and the derived quantities for the next iteration, one lane per parameter; the loss on one more
         // lane.  The divergent code paths (prior, loss, sin/cos of the yaw, sigmoid of the shapes) sit on different
@@ -521,8 +551,8 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
         {
             int k = -1;
             if (warp == 0 && lane < 7 && lane != 3) k = lane;       // translation, scales (+ prior)
-            if (warp == 3 % nwarps && lane == 3) k = 3;             // yaw -> sin, cos
-            if (warp == 2 % nwarps && (lane == 7 || lane == 8)) k = lane;  // shapes -> sigmoid
+            if (warp == min(3, nwarps - 1) && lane == 3) k = 3;     // yaw -> sin, cos
+            if (warp == min(2, nwarps - 1) && (lane == 7 || lane == 8)) k = lane;  // shapes -> sigmoid
             const bool loss_lane = warp == 1 && lane == 9;
             if (k >= 0) {
                 float g = red[0][k];
@@ -562,8 +592,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
             if (k >= 0) {
                 if (k < 7 || A.optimize_shapes) {
                     float g = S.grad[k], m = S.m[k], v = S.v[k], p = S.par[k];
-                    float alpha = A.adam_tab[it * 4 + (k < 7 ? 0 : 1)];
-                    float bc2s = A.adam_tab[it * 4 + 2];
+                    const float alpha = S.adam_now[k < 7 ? 0 : 1], bc2s = S.adam_now[2];
                     m = __fmaf_rn(A.beta1w, __fsub_rn(g, m), m);
                     v = __fmul_rn(v, A.beta2);
                     v = __fmaf_rn(__fmul_rn(A.beta2w, g), g, v);
@@ -575,6 +604,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
                 derive_param(S, k);
             }
         }
+        SQ_MARK(S, tid, 14);
         if (last && crank == 0) {
             if (A.out_eta_idx) for (int i = tid; i < kN; i += T) A.out_eta_idx[(size_t)obj * kN + i] = S.pj[i];
             if (A.out_grids) for (int i = tid; i < kG; i += T) {
@@ -587,7 +617,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
     }
     if (tid == 0) S.cyc[11] = S.ge.rebuilds + S.go.rebuilds;  // slot 11: tree rebuilds (both grids)
     __syncthreads();
-    if (A.out_cycles && crank == 0 && tid < 12) A.out_cycles[(size_t)obj * 12 + tid] = S.cyc[tid];
+    if (A.out_cycles && crank == 0 && tid < 16) A.out_cycles[(size_t)obj * 16 + tid] = S.cyc[tid];
     if (tid < 9 && crank == 0) {
         float p = S.par[tid];
         A.out_params[(size_t)obj * 9 + tid] = p;

@@ -9,6 +9,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from odam_b200 import api, synthetic  # noqa: E402
@@ -44,13 +45,15 @@ for k in range(a.launches):
           f"{api.algorithmic_flops(tracks.view_off[1:] - tracks.view_off[:-1], iters) / ms / 1e9:.2f} TFLOP/s")
 print("flagged", int((out["status"].cpu() & 3 != 0).sum()))
 if a.cycles:
-    cyc = torch.zeros((tracks.n, 12), dtype=torch.int64, device="cuda:0")
+    cyc = torch.zeros((tracks.n, 16), dtype=torch.int64, device="cuda:0")
     api.optimize_device(dt, n_iters=iters, threads=a.threads, max_slices=a.max_slices, out=out, cycles=cyc, cluster=a.cluster, code_layout=a.layout)
     torch.cuda.synchronize()
     c = cyc.cpu().numpy().astype(float) / iters
-    names = ["-", "B fix-up walk (eta)", "D points", "E project", "F backward + warp reduce", "-", "G reduce (+cluster), Adam, derive", "C cdf",
-             "B0 eta (powers, ratios, placement)", "-", "wait for omega warps", "rebuilds (count)"]
+    names = ["F: combine slices", "B fix-up walk (eta)", "D points", "E project", "F: butterfly + barrier", "F: resolve arg + exact re-evaluation", "G: end-of-iteration barrier", "C cdf",
+             "B0 eta (powers, ratios, placement)", "F: loss term + gradient", "wait for omega warps", "rebuilds (count)",
+             "G: cross-warp sum + cluster exchange", "G: barrier", "G: gradient, Adam, derive (warp 0)", "-"]
     print("mean SM cycles per iteration per object (thread 0's view):")
-    for k in range(11):
-        print(f"  {names[k]:30s} {c[:, k].mean():9.0f}  ({c[:, k].mean() / c.sum(1).mean():5.1%})")
-    print(f"  total          {c.sum(1).mean():9.0f}")
+    tot = np.delete(c, 11, axis=1).sum(1).mean()
+    for k in [8, 1, 7, 10, 2, 3, 0, 5, 9, 4, 12, 13, 14, 6]:
+        print(f"  {names[k]:40s} {c[:, k].mean():9.0f}  ({c[:, k].mean() / tot:5.1%})")
+    print(f"  {'total':40s} {tot:9.0f}     tree rebuilds per object: {c[:, 11].mean() * iters:.1f}")
