@@ -51,26 +51,69 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML polled every 5 ms from a
+    thread of this process (an `nvidia-smi -lms` child needs ~100 ms to deliver its first sample, longer than a short
+    timed region); `nvidia-smi` is the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.path = os.path.join(tempfile.gettempdir(), f"odam_clocks_{os.getpid()}.csv")
-        self.gpu, self.proc = gpu_index, None
+        self.gpu, self.uuid, self.proc, self.thread = gpu_index, uuid, None, None
+        self.sm, self.mask, self.smax, self.source = [], 0, None, None
+
+    def _poll(self, nv, h):
+        import threading
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(get_reasons(h))
+            except nv.NVMLError:
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
+                except nv.NVMLError:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._stop = threading.Event()
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.source = "nvml, 5 ms period"
+            return
+        except Exception:  # noqa: BLE001 - no binding / no NVML: fall back to the nvidia-smi child
+            self.thread = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi -lms 20"
         except OSError:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.smax, samples=len(self.sm),
+                           reasons=sorted(k for k, b in self.BITS.items() if self.mask & b))
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -195,7 +238,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
-def time_config(api, torch, dt, n_iters, steps, warmup, flush, dist=None, gath=None):
+def time_config(api, torch, dt, n_iters, steps, warmup, flush, dist=None, gath=None, sampler=None):
     """K device-resident steps with CUDA events on torch's current stream (= the launching stream).
     Returns (per-step ms list for the whole step, per-step ms list for the kernel alone)."""
     out = api.optimize_device(dt, n_iters=n_iters)
@@ -206,6 +249,8 @@ def time_config(api, torch, dt, n_iters, steps, warmup, flush, dist=None, gath=N
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    if sampler is not None:
+        sampler.start()   # clocks are sampled from here on: the timed steps (and the e2e steps that follow)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     for k in range(steps):
         flush.zero_()  # L2 flush between timed iterations (256 MiB > 126 MB L2), outside the event pair
@@ -247,10 +292,9 @@ def run_native(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gath = torch.empty((world * tracks.n, 9), dtype=torch.float32, device=dev) if world > 1 else None
 
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    step_ms, kern_ms, out = time_config(api, torch, dt, n_iters, args.steps, args.warmup, flush, dist, gath)
+    clocks = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
+    step_ms, kern_ms, out = time_config(api, torch, dt, n_iters, args.steps, args.warmup, flush, dist, gath,
+                                        clocks if rank == 0 else None)
     tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
