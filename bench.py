@@ -51,92 +51,68 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML polled every 5 ms from a
-    thread of this process (an `nvidia-smi -lms` child needs ~100 ms to deliver its first sample, longer than a short
-    timed region); `nvidia-smi` is the fallback when the NVML binding is missing."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+
+    An `nvidia-smi -lms` child needs ~100 ms to deliver its first sample -- longer than a short timed region -- so it is
+    launched when the bench starts and its time-stamped samples are cut to the window [begin(), stop()] afterwards.
+    (Polling NVML from a thread of this process was tried and rejected: it slowed the 2-GPU step by 14 %.)"""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
-    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index, uuid=None):
+    def __init__(self, gpu_index, period_ms=10):
         self.path = os.path.join(tempfile.gettempdir(), f"odam_clocks_{os.getpid()}.csv")
-        self.gpu, self.uuid, self.proc, self.thread = gpu_index, uuid, None, None
-        self.sm, self.mask, self.smax, self.source = [], 0, None, None
+        self.gpu, self.period, self.proc, self.t0 = gpu_index, period_ms, None, None
 
-    def _poll(self, nv, h):
-        import threading
-        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-        while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mask |= int(get_reasons(h))
-            except nv.NVMLError:
-                pass
-            self._stop.wait(0.005)
-
-    def start(self):
-        try:
-            import threading
-            import pynvml as nv
-            nv.nvmlInit()
-            h = None
-            if self.uuid:
-                try:
-                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(self.uuid)).encode())
-                except nv.NVMLError:
-                    h = None
-            if h is None:
-                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
-            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            self._stop = threading.Event()
-            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
-            self.thread.start()
-            self.source = "nvml, 5 ms period"
-            return
-        except Exception:  # noqa: BLE001 - no binding / no NVML: fall back to the nvidia-smi child
-            self.thread = None
+    def launch(self):
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period)], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
-            self.source = "nvidia-smi -lms 20"
         except OSError:
             self.proc = None
 
+    def start(self):   # the timed region begins
+        import datetime
+        self.t0 = datetime.datetime.now()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
-        if self.thread is not None:
-            self._stop.set()
-            self.thread.join(timeout=2)
-            if self.sm:
-                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.smax, samples=len(self.sm),
-                           reasons=sorted(k for k, b in self.BITS.items() if self.mask & b))
-            return out
+        import datetime
+        t1 = datetime.datetime.now()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+               "source": f"nvidia-smi -lms {self.period}, samples inside the timed window"}
         if self.proc is None:
             return out
+        time.sleep(2.5 * self.period / 1e3)   # let the last sample of the window reach the file
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
         self.f.close()
-        sm, reasons, smax = [], set(), None
+        rows = []
         for line in open(self.path):
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); smax = float(c[2])
+                rows.append((datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f"), float(c[1]), float(c[2]), c[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+        os.unlink(self.path)
+        lo = (self.t0 or t1) - datetime.timedelta(milliseconds=self.period)
+        inside = [r for r in rows if lo <= r[0] <= t1 + datetime.timedelta(milliseconds=2 * self.period)]
+        if not inside and rows:   # clock skew or a very short window: fall back to the samples nearest to it
+            inside, out["source"] = rows[-3:], out["source"] + " (none inside: last samples before the stop)"
+        reasons = set()
+        for r in inside:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=inside[-1][2],
+                       reasons=sorted(reasons), samples=len(inside))
         return out
 
 
@@ -283,6 +259,9 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from odam_b200 import _lib, api
     _lib.check(_lib.load().odam_sq_init(local_rank))
+    clocks = ClockSampler(local_rank)
+    if rank == 0 and args.clocks != "off":
+        clocks.launch()   # running by the time the timed region starts; cut to that window afterwards
 
     cfg, scene, tracks, prior = workload(args.config, rank, args.objects, device=dev)
     n_iters = cfg["n_iters"]
@@ -292,9 +271,8 @@ def run_native(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gath = torch.empty((world * tracks.n, 9), dtype=torch.float32, device=dev) if world > 1 else None
 
-    clocks = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     step_ms, kern_ms, out = time_config(api, torch, dt, n_iters, args.steps, args.warmup, flush, dist, gath,
-                                        clocks if rank == 0 else None)
+                                        clocks if rank == 0 and args.clocks != "off" else None)
     tot = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
@@ -419,6 +397,7 @@ def main():
     ap.add_argument("--sweep", type=int, nargs="*", default=[3, 4, 5])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--clocks", default="smi", choices=["smi", "off"], help="clock sampler (off: diagnostics only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-iters", type=int, default=20)
     args = ap.parse_args()
