@@ -20,6 +20,36 @@ def lib():
     return _lib.load()
 
 
+def test_header_is_plain_c_and_links(lib, tmp_path):
+    """The boundary is a C ABI: the header compiles as strict C99 and a C program links against the library
+    (no C++ or torch types in the signatures).  The program only calls the no-GPU housekeeping entries."""
+    from odam_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text('''#include <stdio.h>
+#include <string.h>
+#include "odam_sq.h"
+int main(void) {
+    odam_sq_options o;
+    memset(&o, 0, sizeof o);
+    int32_t voff[3] = {0, 20, 40};
+    int threads = 0, layout = 0, slices = 0;
+    if (odam_sq_abi_version() != ODAM_SQ_ABI_VERSION) return 1;
+    if (odam_sq_query_launch(voff, 2, &o, &threads, NULL, NULL, NULL, &layout, &slices) != 0) return 2;
+    if (odam_sq_optimize_host(NULL, NULL, NULL, NULL, NULL, NULL, NULL, 1, 1, 0, 0.01f, 0.1f, NULL, NULL, NULL, NULL, 0) >= 0) return 3;
+    printf("%d %d %d %s\\n", threads, layout, slices, odam_sq_error_string(-1));
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(REPO, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-lodam_sq", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    threads, layout, slices = (int(x) for x in r.stdout.split()[:3])
+    assert threads % 32 == 0 and layout in (1, 2) and 1 <= slices <= 25
+
+
 def test_header_symbols_exported(lib):
     hdr = open(os.path.join(REPO, "include", "odam_sq.h")).read()
     declared = set(re.findall(r"\b(odam_sq_[a-z_0-9]+)\s*\(", hdr))
