@@ -50,6 +50,13 @@ int main(void) {
     assert threads % 32 == 0 and layout in (1, 2) and 1 <= slices <= 25
 
 
+def test_graft_entry_build():
+    """The driver's "does it build" check: every native piece compiles for sm_100a and the package imports."""
+    sys.path.insert(0, REPO)
+    import __graft_entry__
+    __graft_entry__.build()
+
+
 def test_header_symbols_exported(lib):
     hdr = open(os.path.join(REPO, "include", "odam_sq.h")).read()
     declared = set(re.findall(r"\b(odam_sq_[a-z_0-9]+)\s*\(", hdr))
