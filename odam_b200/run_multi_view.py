@@ -77,9 +77,10 @@ def optim_process(tracks, img_names, T_wcs, P_cws, img_h, img_w, K, representati
     P_cws = np.asarray(P_cws)
     staged = [stage_object(t, img_names, img_h, img_w) for t in tracks]
     optimizers, bboxes_dl = [], []
-    for s in staged:
+    # run_multi_view.py:57: the z angle of every averaged pose (one scipy call for all objects)
+    yaws = Rotation.from_matrix(np.stack([s["R"] for s in staged])).as_euler("zxy")[:, 0] if staged else []
+    for s, yaw in zip(staged, yaws):
         bboxes_dl.append(get_3d_box(s["dims"], s["R"], s["t_wo"]))
-        yaw = Rotation.from_matrix(s["R"]).as_euler("zxy")[0]
         o = SuperQuadricOptimizer(s["t_wo"], yaw, s["dims"], s["obj_class"], representation, prior)
         o.device = device
         optimizers.append(o)

@@ -82,6 +82,31 @@ class SuperQuadric:
         return torch.stack([cosz, -sinz, zeros, sinz, cosz, zeros, zeros, zeros, ones], dim=0).reshape(3, 3)
 
 
+class LossLog(list):
+    """``loss_log`` of the reference (sq_libs.py:471): a list with one ``[tensor(total loss)]`` entry per iteration.
+    The values arrive from the GPU as one float32 array per run; they are kept as Python floats and wrapped into the
+    reference's ``[tensor]`` form when read (creating 10 000 scalar tensors eagerly costs several times the
+    optimisation itself).  ``len``, indexing, slicing, iteration, ``append`` and ``extend`` behave like the list's."""
+
+    @staticmethod
+    def _wrap(v):
+        return v if isinstance(v, list) else [torch.tensor(v, dtype=torch.float32)]
+
+    def extend_values(self, values):
+        list.extend(self, (float(v) for v in values))
+
+    def __getitem__(self, i):
+        v = list.__getitem__(self, i)
+        return [self._wrap(x) for x in v] if isinstance(i, slice) else self._wrap(v)
+
+    def __iter__(self):
+        return (self._wrap(v) for v in list.__iter__(self))
+
+    def values(self):
+        """float32 array of the losses logged so far (entries appended by hand in the reference's form included)."""
+        return np.array([float(v[0]) if isinstance(v, list) else v for v in list.__iter__(self)], np.float32)
+
+
 class _AdamState:
     """What the drop-in keeps of ``torch.optim.Adam``: moments and step count (packed like the parameters)."""
 
@@ -113,7 +138,7 @@ class SuperQuadricOptimizer:
         # reference sq_libs.py:388-392: ./src/super_quadric/scale_prior relative to the cwd; the packaged export of
         # the same data file is used when that path does not exist
         self.scale_prior = {k: torch.tensor(v).float() for k, v in api.load_scale_prior().items()}
-        self.loss_log = []
+        self.loss_log = LossLog()
         self.device = 0
 
     # -- packing ----------------------------------------------------------------------------------------
@@ -188,7 +213,7 @@ def optimize_batch(optimizers, gt_lines_list, Ms_list, n_iters=200, device=None,
         o.Q_init._set_params(out["params"][i])
         o.optimizer.exp_avg, o.optimizer.exp_avg_sq = out["out_m"][i].copy(), out["out_v"][i].copy()
         o.optimizer.step += n_iters
-        o.loss_log.extend([[torch.tensor(float(l))] for l in out["loss"][i]])  # list of 1-element lists, as :471
+        o.loss_log.extend_values(out["loss"][i])   # read back as a list of 1-element [tensor] lists, as :471
     if bad.size:
         raise RuntimeError(f"superquadric optimisation produced NaN/Inf for object(s) {bad.tolist()} "
                            "(the reference raises from torch anomaly mode, sq_libs.py:456)")

@@ -161,6 +161,21 @@ def test_optimizer_constructor_mirrors_reference():
     assert np.array_equal(q2.params(), q.params())
 
 
+def test_loss_log_reads_like_the_references_list():
+    """loss_log keeps floats and hands out the reference's [tensor] entries (sq_libs.py:471) when read."""
+    import torch
+    from odam_b200.sq_libs import LossLog
+    log = LossLog()
+    assert log == [] and len(log) == 0
+    log.extend_values(np.array([1.5, 0.25, 3.0], np.float32))
+    log.append([torch.tensor(7.0)])   # the reference's own form still works
+    assert len(log) == 4 and isinstance(log, list)
+    assert isinstance(log[0], list) and torch.is_tensor(log[0][0]) and log[0][0].dtype == torch.float32
+    assert [float(e[0]) for e in log] == [1.5, 0.25, 3.0, 7.0]
+    assert [float(e[0]) for e in log[1:3]] == [0.25, 3.0] and float(log[-1][0]) == 7.0
+    assert np.array_equal(log.values(), np.array([1.5, 0.25, 3.0, 7.0], np.float32))
+
+
 def test_call_site_staging_matches_reference():
     """stage_object / get_3d_box / compute_oriented_bbox against outputs of the reference's own helpers."""
     from odam_b200 import api
