@@ -78,6 +78,40 @@ def record_reference_run(sq, scene, i, representation, prior, n_iters, V=None):
     return rec
 
 
+def prepare_tracks_fixture(sq):
+    """The body of OdamProcess._prepare_tracks' loop (reference src/processor.py:188-205) run with the reference's own
+    SuperQuadric / geometry helpers on synthetic tracks: per track the projected box of its mean-pose quadric in one
+    camera.  (The method itself needs the detector/associator state of OdamProcess; the loop body is what the
+    drop-in's odam_b200.processor.prepare_track_boxes mirrors.)"""
+    import src.utils.geometry_utils as geo_utils
+    from odam_b200 import synthetic
+    rng = np.random.default_rng(88)
+    K = synthetic.K
+    # a camera 3 m back, 1.4 m up, looking at the origin region (+z up world)
+    eye, at = np.array([3.0, 0.4, 1.4]), np.array([0.0, 0.0, 0.4])
+    f = (at - eye) / np.linalg.norm(at - eye); r = np.cross(f, [0, 0, 1.0]); r /= np.linalg.norm(r); d = np.cross(f, r)
+    T_wc = np.eye(4); T_wc[:3, 0], T_wc[:3, 1], T_wc[:3, 2], T_wc[:3, 3] = r, d, f, eye
+    out = dict(T_wc=T_wc, K=K)
+    for t in range(6):
+        nrow = int(rng.integers(1, 12))
+        track = -np.ones((nrow, 82))
+        track[:, 6:9] = rng.uniform(0.02 if t == 5 else 0.3, 1.5, 3)[None] + rng.normal(0, 0.02, (nrow, 3))   # t=5: clipped dims
+        track[:, 9:12] = rng.uniform(-0.8, 0.8, 3)[None] * np.array([1, 1, 0.3]) + rng.normal(0, 0.05, (nrow, 3))
+        track[:, 12] = rng.uniform(-np.pi, np.pi) + rng.normal(0, 0.1, nrow)
+        azi_wo = np.mean(track[:, 12], axis=0)
+        t_wo = np.mean(track[:, 9: 12], axis=0)
+        dimensions = np.clip(np.mean(track[:, 6: 9], axis=0), a_min=0.05, a_max=np.inf)
+        Q = sq.SuperQuadric(t_wo, azi_wo, np.sqrt(dimensions / 2), shapes=np.array([-0., -0.]))
+        pts, _ = Q.compute_ellipsoid_points(use_numpy=True)
+        box_3d_c = (geo_utils.get_homogeneous(pts) @ np.linalg.inv(T_wc).T)[:, :3]
+        pixels = geo_utils.projection(box_3d_c, K)
+        x_min, y_min, _ = np.min(pixels, axis=0)
+        x_max, y_max, _ = np.max(pixels, axis=0)
+        out.update({f"t{t}_track": track, f"t{t}_pts": pts, f"t{t}_box": np.array([x_min, y_min, x_max, y_max])})
+    np.savez_compressed(os.path.join(OUT, "prepare_tracks.npz"), **out)
+    print("wrote prepare_tracks.npz")
+
+
 def main():
     b = build_reference_extension()
     sys.path[:0] = [REF, b]
@@ -85,6 +119,9 @@ def main():
     import torch
     torch.set_num_threads(1)
     import src.super_quadric.sq_libs as sq
+    if "--only-prepare-tracks" in sys.argv:   # add this fixture without regenerating the others
+        prepare_tracks_fixture(sq)
+        return
     from learnable_primitives.fast_sampler import fast_sample_on_batch
     from oracle import c_oracle, torch_oracle
     from odam_b200 import synthetic
@@ -214,6 +251,7 @@ def main():
         cs[f"obb{k}_pts"] = out[f"c{k}_final_points"]
         cs[f"obb{k}_box"] = box_utils.compute_oriented_bbox(out[f"c{k}_final_points"].astype(np.float64))
     np.savez_compressed(os.path.join(OUT, "call_site.npz"), **cs)
+    prepare_tracks_fixture(sq)
     print("wrote", OUT)
 
 

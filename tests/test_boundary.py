@@ -161,6 +161,23 @@ def test_optimizer_constructor_mirrors_reference():
     assert np.array_equal(q2.params(), q.params())
 
 
+def test_prepare_tracks_projection_matches_reference():
+    """odam_b200.processor against the reference's own _prepare_tracks loop body (tests/golden/prepare_tracks.npz):
+    the float64 camera transform / projection / min-max is bit-identical on the reference's points, and the
+    mean-pose quadric (dims clipped at 0.05) gives the reference's surface to fp32 rounding."""
+    from odam_b200 import processor
+    from oracle import c_oracle
+    c_oracle.build()
+    G = np.load(os.path.join(REPO, "tests", "golden", "prepare_tracks.npz"))
+    for t in range(6):
+        box = processor.project_points_reference_way(G[f"t{t}_pts"], G["T_wc"], G["K"])
+        assert np.array_equal(box, G[f"t{t}_box"]), t
+        P = processor.track_quadric_params([G[f"t{t}_track"]])
+        pts = c_oracle.points(P[0]).astype(np.float32)
+        assert np.abs(pts - G[f"t{t}_pts"]).max() <= 5e-7, t
+        assert np.abs(processor.project_points_reference_way(pts, G["T_wc"], G["K"]) - G[f"t{t}_box"]).max() <= 1e-3
+
+
 def test_loss_log_reads_like_the_references_list():
     """loss_log keeps floats and hands out the reference's [tensor] entries (sq_libs.py:471) when read."""
     import torch

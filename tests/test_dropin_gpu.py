@@ -1,6 +1,7 @@
 """GPU tests of the reference-facing Python interface (odam_b200.sq_libs / run_multi_view): these read like the
 reference's own usage -- construct SuperQuadricOptimizer, call run(gt_lines, None, Ms, n_iters), look at Q_init and
 loss_log -- and compare with the reference's recorded outputs (tests/golden/) or the CPU oracle."""
+import os
 import pickle
 
 import numpy as np
@@ -118,3 +119,19 @@ def test_optim_process_batched_call_site():
     assert np.array_equal(out["bboxes_qc"][3], out["bboxes_dl"][3])
     assert not np.array_equal(out["bboxes_qc"][0], out["bboxes_dl"][0])
     assert out["quadrics"][0].obj_class == int(scene.cls[0])
+
+
+def test_prepare_track_boxes_matches_reference():
+    """The per-frame track projection (reference processor.py:188-205) with all surfaces from one GPU launch, against
+    the boxes the reference's own loop body produced for the same tracks and camera (pixels; fp32 surface rounding
+    moves a box side by < 1e-4 px)."""
+    from odam_b200.processor import prepare_track_boxes
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prepare_tracks.npz"))
+    tracks = [G[f"t{t}_track"] for t in range(6)]
+    before = [t.copy() for t in tracks]
+    out = prepare_track_boxes(tracks, G["T_wc"], G["K"])
+    for t in range(6):
+        assert np.array_equal(tracks[t], before[t])                        # inputs untouched (the reference deep-copies)
+        assert np.array_equal(out[t][:, :-4], before[t][:, :-4])
+        assert np.abs(out[t][:, -4:] - G[f"t{t}_box"][None]).max() <= 1e-3, t
+    assert prepare_track_boxes([], G["T_wc"], G["K"]) == []
