@@ -885,22 +885,24 @@ struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_off
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
                          int smem_optin, LaunchCfg &L)
 {
-    // point slices per view: many for a lone CTA (latency), 8 when CTAs share SMs (16 for very short tracks)
-    int max_slices = opt && opt->max_slices ? opt->max_slices : (n >= sm_count ? (mean_views < 12 ? 16 : 8) : 25);
-    if (max_slices < 1 || max_slices > 25) return ODAM_SQ_ERR_ARG;
-    // view-tiled clusters: when there are fewer objects than SMs, 2 or 4 CTAs (on different SMs) share an object;
-    // long tracks (>= 128 views) are split in two in any case (finer load balance across SMs)
+    // view-tiled clusters: while every CTA can still have an SM to itself, 2 or 4 CTAs (on different SMs) share an
+    // object; long tracks (>= 128 views) are split in two in any case (finer load balance across SMs)
     int cluster = opt ? opt->cluster : 0;
     if (cluster == 0)
         cluster = (4 * n <= sm_count && mean_views >= 32) ? 4
-                  : (((2 * n <= sm_count + 32 && mean_views >= 16) || mean_views >= 128) ? 2 : 1);
+                  : (((2 * n <= sm_count && mean_views >= 16) || mean_views >= 128) ? 2 : 1);
     if (cluster != 1 && cluster != 2 && cluster != 4) return ODAM_SQ_ERR_ARG;
+    // two regimes (measured, tools/regime_sweep.sh): "latency" = no more CTAs than SMs, one wide CTA per SM;
+    // "dense" = CTAs share SMs, 256-thread CTAs
+    const bool dense = n * cluster > sm_count;
+    // point slices per view: many for a lone CTA, 8 when CTAs share SMs (16 for very short tracks)
+    int max_slices = opt && opt->max_slices ? opt->max_slices : (dense ? (mean_views < 12 * cluster ? 16 : 8) : 25);
+    if (max_slices < 1 || max_slices > 25) return ODAM_SQ_ERR_ARG;
     mean_views = std::max(1.0, mean_views / cluster);
     max_views = (max_views + cluster - 1) / cluster;
     int threads = opt ? opt->threads : 0;
     // code layout: compact when several CTAs in different phases share an SM and the sampler/backward phases are a
     // sizeable part of the iteration (few views); long tracks spend their time in the projection loop either way
-    const bool dense = n * cluster >= 2 * sm_count;
     int layout = opt ? opt->code_layout : 0;
     if (layout < 0 || layout > 2) return ODAM_SQ_ERR_ARG;
     if (layout == 0) layout = (dense && mean_views <= kCompactMaxViews && (threads == 0 || threads <= 256)) ? 2 : 1;
@@ -922,7 +924,7 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     long smem = red_offset + (threads / 32) * (kRed + 3) * 4;            // + cross-warp reduction rows
     // latency regime (few, wide CTAs: shared memory is plentiful): stage each CTA's views by TMA, 68 bytes per view
     long stage_offset = (smem + 15) & ~15L;
-    int stage_views = (n * cluster < 2 * sm_count && max_views <= 256) ? ((max_views + 3) & ~3) : 0;
+    int stage_views = (!dense && max_views <= 256) ? ((max_views + 3) & ~3) : 0;
     if (stage_views) smem = stage_offset + (long)stage_views * 68;
     if (smem + (long)sizeof(Smem) > smem_optin) return ODAM_SQ_ERR_CONFIG;
     L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem; L.cluster = cluster; L.red_offset = (int)red_offset;
