@@ -24,6 +24,10 @@
 #include <vector>
 
 #include "../../include/odam_sq.h"
+
+#ifndef SQ_FFMA2
+#define SQ_FFMA2 1   // phase E on packed fp32 pairs (FFMA2/FMUL2); 0 = scalar FFMA build for A/B timing
+#endif
 #include "sq_device.cuh"
 
 namespace cg = cooperative_groups;
@@ -249,10 +253,15 @@ __device__ __forceinline__ void scan_item(const Smem &S, const float (&M)[12], i
 #pragma unroll
             for (int h = 0; h < kGroup / 4; h++) {
                 float4 x = xs[h], y = ys[h], z = zs[h];
+#if SQ_FFMA2
+                project_uv2<kCheck>(M, x.x, x.y, y.x, y.y, z.x, z.y, u[4 * h + 0], u[4 * h + 1], w[4 * h + 0], w[4 * h + 1]);
+                project_uv2<kCheck>(M, x.z, x.w, y.z, y.w, z.z, z.w, u[4 * h + 2], u[4 * h + 3], w[4 * h + 2], w[4 * h + 3]);
+#else
                 project_uv<kCheck>(M, x.x, y.x, z.x, u[4 * h + 0], w[4 * h + 0]);
                 project_uv<kCheck>(M, x.y, y.y, z.y, u[4 * h + 1], w[4 * h + 1]);
                 project_uv<kCheck>(M, x.z, y.z, z.z, u[4 * h + 2], w[4 * h + 2]);
                 project_uv<kCheck>(M, x.w, y.w, z.w, u[4 * h + 3], w[4 * h + 3]);
+#endif
             }
 #pragma unroll
             for (int h = 0; h < kGroup; h += 2) {

@@ -141,10 +141,40 @@ def make_scene(n_objects, n_views, seed, device="cpu", oversample=2.0):
         raise RuntimeError(f"{bad.size} objects have fewer than {V} usable views; raise oversample")
     take = lambda x: np.take_along_axis(x, order.reshape(n, V, *([1] * (x.ndim - 2))), 1)
     box, keep, P = take(box), take(keep), take(P)
+    T_wc = np.zeros((n, Vd, 4, 4))
+    T_wc[..., :3, :3], T_wc[..., :3, 3], T_wc[..., 3, 3] = R_wc, eye, 1.0
+    box_raw = box.copy()
     box = np.where(keep, box, 0.0)
     return Scene(translate=init_t, angle=init_yaw, dims=init_dims, cls=cls, P_cws=P, box=box,
                  mask=keep.astype(np.uint8),
-                 gt=dict(centre=centre, yaw=yaw, dims=dims, logits=logits))
+                 gt=dict(centre=centre, yaw=yaw, dims=dims, logits=logits, T_wcs=take(T_wc), box_raw=box_raw))
+
+
+def scene_to_tracks(scene, rows_per_object=None, seed=0):
+    """A Scene as the inputs of the reference's call site ``optim_process`` (run_multi_view.py:22): every object owns
+    its own block of frames (object i is seen in frames i*V .. i*V+V-1 of one long sequence), one 82-float track row
+    per (object, frame) in the layout of processor.py:98-108 -- [0] frame id, [1] class, [2:6] box x_min,y_min,x_max,
+    y_max in pixels, [6:9] dims, [9:12] centre, [12] yaw, [13] score, rest -1.  Per-row detector noise on dims, centre
+    and yaw is drawn around the scene's initial values, so the averaged pose the call site derives is close to them.
+    rows_per_object[i] < V keeps only the first rows (an object seen in too few frames is not optimised).
+    Returns dict(tracks, img_names, T_wcs, P_cws, img_h, img_w, K)."""
+    rng = np.random.default_rng(seed)
+    n, V = scene.n, scene.V
+    tracks = []
+    for i in range(n):
+        rows = V if rows_per_object is None else int(rows_per_object[i])
+        t = -np.ones((rows, 82))
+        t[:, 0] = i * V + np.arange(rows)
+        t[:, 1] = scene.cls[i]
+        b = scene.gt["box_raw"][i, :rows]
+        t[:, 2:6] = np.stack([b[:, 0], b[:, 2], b[:, 1], b[:, 3]], 1)
+        t[:, 6:9] = scene.dims[i][None] * rng.uniform(0.97, 1.03, (rows, 3))
+        t[:, 9:12] = scene.translate[i][None] + rng.normal(0, 0.02, (rows, 3))
+        t[:, 12] = scene.angle[i] + rng.normal(0, 0.03, rows)
+        t[:, 13] = rng.uniform(0.5, 1.0, rows)
+        tracks.append(t)
+    return dict(tracks=tracks, img_names=np.arange(n * V), T_wcs=scene.gt["T_wcs"].reshape(n * V, 4, 4),
+                P_cws=scene.P_cws.reshape(n * V, 3, 4), img_h=IMG_H, img_w=IMG_W, K=K)
 
 
 # BASELINE.json configs -> (objects, views, iterations, prior); seed = config index (SURVEY 8d)

@@ -24,6 +24,17 @@ def sampler_kat():
     return np.load(os.path.join(REPO, "tests", "golden", "sampler_kat.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_wide():
+    import numpy as np
+    return np.load(os.path.join(REPO, "tests", "golden", "ref_runs_wide.npz"))
+
+
+def golden(name):
+    import numpy as np
+    return np.load(os.path.join(REPO, "tests", "golden", name))
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _native_libraries_built():
     """Build (or refresh) the product library and the checker libraries once per session; both are no-ops when the

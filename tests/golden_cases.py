@@ -52,3 +52,32 @@ class Case:
 
 def all_cases(G):
     return [Case(G, k) for k in range(len(G["case_obj"]))]
+
+
+class WideCase(Case):
+    """A case of tests/golden/ref_runs_wide.npz (round 2: the BASELINE view counts and the loop's edge cases); every
+    case carries its own views, so nothing is indexed through a shared scene."""
+
+    def __init__(self, W, k):
+        self.k = k
+        self.name = str(W["names"][k])
+        self.repr = str(W["case_repr"][k])
+        self.use_prior = bool(W["case_prior"][k])
+        self.iters = int(W["case_iters"][k])
+        self.V = V = int(W["case_views"][k])
+        self.Ms64, self.box64 = W[f"w{k}_Ms"], W[f"w{k}_box"]
+        self.Ms = np.ascontiguousarray(self.Ms64.reshape(V, 12), np.float32)
+        self.box = np.ascontiguousarray(self.box64, np.float32)
+        self.mask = np.ascontiguousarray(W[f"w{k}_mask"], np.uint8)
+        self.cls = int(W[f"w{k}_cls"])
+        self.translate, self.angle, self.dims = W[f"w{k}_translate"], float(W[f"w{k}_angle"]), W[f"w{k}_dims"]
+        self.prior33 = W["prior_by_class"][self.cls] if self.use_prior else None
+        self.prior_table = np.stack([W["prior_by_class"][c].astype(np.float32).reshape(9) for c in range(8)]) \
+            if self.use_prior else None
+        self.init = W[f"w{k}_init"]
+        for x in ("params", "grad", "m", "v", "loss", "final_points", "arg", "eta_idx", "resid_sign"):
+            setattr(self, x, W[f"w{k}_{x}"])
+
+
+def wide_cases(W):
+    return [WideCase(W, k) for k in range(len(W["names"]))]
