@@ -20,8 +20,13 @@ roofline  FP32: algorithmic flops (iters*(37,000*V+30,000) per object
 cpu_baseline / --impl reference   the reference's optimiser loop (oracle/torch_oracle.py, an op-for-op port
         pinned bit-for-bit to the reference; with oracle/_ref's compiled reference sampler when present) on the
         host cores, on a bounded sample of the same workload.
-Multi-GPU: weak scaling -- every rank optimises its own scene of the named shape (objects are independent, no
-data-path collective) and the final parameters are all-gathered over NCCL inside the timed step.
+sfu     roofline.sfu: one MUFU.RCP per point-view (1000 per unit) against 148 SMs x 16 SFU lanes x clock.
+e2e_call_site   the reference-facing entry point itself: 82-column tracks -> odam_b200.run_multi_view.optim_process ->
+        result dict (staging, H2D, kernel, D2H, oriented boxes on the device, result objects), host buffers throughout.
+Multi-GPU: the headline stays weak scaling -- every rank optimises its own scene of the named shape (objects are
+independent, no data-path collective) and the final parameters are all-gathered over NCCL inside the timed step -- and
+`strong` carries what north_star names: ONE batch (BASELINE configs 3 and 5) sharded by object across the N ranks
+(contiguous blocks balanced by views, odam_b200.sharding), each rank's block in one launch, one all-gather of [n, 9].
 """
 import argparse
 import json
@@ -150,6 +155,45 @@ def cpu_jobs(scene, tracks, prior, objs, iters, threads):
     return jobs
 
 
+def map_reference_sampler():
+    """dlopen oracle/_ref in THIS process too: the workers that use it are short-lived, and the driver records which
+    native libraries the bench process itself has mapped."""
+    import ctypes
+    from oracle import c_oracle
+    if c_oracle.have_ref_sampler():
+        return ctypes.CDLL(c_oracle.ref_sampler_path())
+    return None
+
+
+def cpu_baseline_config1(budget_s=40.0):
+    """SURVEY 8d / BASELINE configs[0]: 1 scene, 10 objects x 20 views, 200 iterations, prior on, as shipped (anomaly
+    mode on, sequential objects, torch's default intra-op threads).  Runs the whole config (about half a minute) unless
+    the budget runs out first; whole objects only."""
+    import torch
+    from odam_b200 import api, synthetic
+    from oracle import c_oracle
+    c_oracle.build()
+    map_reference_sampler()
+    c = synthetic.CONFIGS[1]
+    scene = synthetic.make_scene(c["n_objects"], c["n_views"], seed=1)
+    tracks = api.pack_scene(scene)
+    prior = api.prior_table()
+    threads = torch.get_num_threads()
+    done, t_total = 0, 0.0
+    for i in range(scene.n):
+        t_total += cpu_port_worker(cpu_jobs(scene, tracks, prior, [i], c["n_iters"], threads)[0])
+        done += 1
+        if t_total > budget_s:
+            break
+    units = done * scene.V * c["n_iters"]
+    return {"value": units / t_total, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"config 1 ({c['name']}, {c['n_iters']} iterations, prior on): {done} of {scene.n} objects, all "
+                      f"{c['n_iters']} iterations, sequential objects as run_multi_view.py:44-69, torch intra-op "
+                      f"threads={threads}, anomaly mode on (as shipped), sampler="
+                      f"{'oracle/_ref (reference C++)' if c_oracle.have_ref_sampler() else 'oracle C restatement'}",
+            "seconds": t_total}
+
+
 def cpu_baseline_sequential(scene, tracks, prior, budget_s=15.0):
     """As the reference runs it (run_multi_view.py:44-69): objects one after another in one process, torch's
     default intra-op threads, anomaly mode on as shipped.  Bounded sample: whole objects at a reduced iteration
@@ -157,6 +201,7 @@ def cpu_baseline_sequential(scene, tracks, prior, budget_s=15.0):
     import torch
     from oracle import c_oracle
     c_oracle.build()
+    map_reference_sampler()
     threads = torch.get_num_threads()
     iters, done, t_total = 40, 0, 0.0
     for i in range(min(scene.n, 64)):
@@ -181,6 +226,7 @@ def run_reference(args):
     import multiprocessing as mp
     from oracle import c_oracle
     c_oracle.build()
+    map_reference_sampler()
     cfg, scene, tracks, prior = workload(args.config, 0, args.objects)
     cores = len(os.sched_getaffinity(0))
     n_obj = min(scene.n, cores)
@@ -287,20 +333,63 @@ def run_native(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        o = api.optimize_host(tracks, prior=prior, n_iters=n_iters, device=local_rank)
-        if world > 1:
-            dist.all_gather_into_tensor(gath, torch.from_numpy(o["params"]).to(dev))
+    if world == 1:
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            api.optimize_host(tracks, prior=prior, n_iters=n_iters, device=local_rank)
+        e2e_path = "odam_b200.api.optimize_host -> odam_sq_optimize_host (pinned staging inside the library)"
+    else:
+        # N GPUs: the same bytes cross the bus, but the step stays on the stream -- H2D of every input from pinned host
+        # memory, one launch, the all-gather of the final parameters on the device, D2H of the gathered parameters and
+        # of this rank's loss log into pinned memory, ONE synchronisation per step
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        host_in = {k: pin(getattr(tracks, k)) for k in ("init", "cls", "view_off", "Ms", "box", "mask")}
+        if prior is not None:
+            host_in["prior"] = pin(prior)
+        dev_in = {k: torch.empty_like(v, device=dev) for k, v in host_in.items()}
+        host_out = {"gath": torch.empty((world * tracks.n, 9), dtype=torch.float32).pin_memory(),
+                    "loss": torch.empty((tracks.n, n_iters), dtype=torch.float32).pin_memory(),
+                    "status": torch.empty((tracks.n,), dtype=torch.int32).pin_memory()}
+        dte = api.DeviceTracks(tracks, dev, prior)
+
+        def e2e_step():
+            for k, v in host_in.items():
+                dev_in[k].copy_(v, non_blocking=True)
+            dte.init, dte.cls, dte.view_off, dte.Ms, dte.box, dte.mask = (dev_in[k] for k in ("init", "cls", "view_off", "Ms", "box", "mask"))
+            if prior is not None:
+                dte.prior = dev_in["prior"]
+            api.optimize_device(dte, n_iters=n_iters, out=out)
+            dist.all_gather_into_tensor(gath, out["params"])
+            host_out["gath"].copy_(gath, non_blocking=True)
+            host_out["loss"].copy_(out["loss"], non_blocking=True)
+            host_out["status"].copy_(out["status"], non_blocking=True)
             torch.cuda.synchronize()
+        e2e_step()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_path = ("pinned host buffers -> H2D -> odam_b200.api.optimize_device (odam_sq_optimize) -> NCCL all-gather on the "
+                    "device -> D2H of gathered parameters + loss log + status, one synchronisation per step")
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     clk = clocks.stop() if rank == 0 else None   # sampled across the device-timed AND the e2e timed regions
     SV, n = tracks.total_views, tracks.n
     h2d = n * 36 + n * 4 + (n + 1) * 4 + SV * (48 + 16 + 4) + (288 if prior is not None else 0) + n_iters * 16
-    d2h = n * 36 + n * n_iters * 4 + n * 4
+    d2h = (world if world > 1 else 1) * n * 36 + n * n_iters * 4 + n * 4
     e2e_value = world * units_rank / (float(e2e_ms[0]) / 1e3)
+
+    # ---- strong scaling: ONE batch sharded by object across the ranks (BASELINE configs 3 and 5) ----
+    strong = []
+    if not args.no_strong:
+        for ci in args.strong:
+            strong.append(strong_scaling(api, torch, dist, ci, rank, world, dev, flush))
+
+    # ---- the reference-facing call site (tracks -> optim_process -> result dict), rank 0 ----
+    call_site = None
+    if rank == 0 and not args.no_call_site:
+        call_site = time_call_site(scene, cfg, local_rank)
 
     if rank != 0:
         if world > 1:
@@ -323,10 +412,19 @@ def run_native(args):
                 "hbm": {"achieved_gbs": algo_bytes / kern_s / 1e9, "peak_gbs": peaks["hbm_gbs"],
                         "frac": algo_bytes / kern_s / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": algo_bytes,
                         "peak_source": peak_src}}
+    sfu_peak = SM_COUNT * 16 * (clk["sm_mhz"] * 1e6 if clk and clk.get("sm_mhz") else NOMINAL_CLOCK_GHZ * 1e9)
+    sfu_ops = float(views.sum()) * n_iters * 1000.0 + tracks.n * n_iters * 12000.0   # 1 rcp per point-view, 12 per point
+    roofline["sfu"] = {"achieved_tops": sfu_ops / kern_s / 1e12, "peak_tops": sfu_peak / 1e12,
+                       "frac": sfu_ops / kern_s / sfu_peak,
+                       "note": "algorithmic SFU-class ops of the reference formulation (SURVEY 8d: 1000 per unit + 12000 per "
+                               "object-iteration; the kernel evaluates the per-point transcendentals once per grid node instead) "
+                               "against 148 SMs x 16 SFU lanes x the SM clock sampled during the run"}
     traffic_file = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
             roofline["traffic"] = json.load(f).get(f"config{args.config}")
+        roofline["traffic_source"] = ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set "
+                                      "full` capture of this config (not re-measured by this run)")
 
     # ---- other BASELINE configs at 1 GPU (short runs; the headline stays the named config) ----
     sweep = []
@@ -336,12 +434,15 @@ def run_native(args):
                 continue
             c2, _, tr2, pr2 = workload(ci, 0, None, device=dev)
             dt2 = api.DeviceTracks(tr2, dev, pr2)
-            s_ms, k_ms, o2 = time_config(api, torch, dt2, c2["n_iters"], 2, 1, flush)
+            est = float(np.diff(tr2.view_off).sum()) * c2["n_iters"] / 6e8          # seconds per step, roughly
+            sw_steps = 10 if est < 0.1 else 3                                         # >= 10 timed steps unless a step is long
+            s_ms, k_ms, o2 = time_config(api, torch, dt2, c2["n_iters"], sw_steps, 3, flush)
             v2 = np.diff(tr2.view_off)
             ks = sum(k_ms) / len(k_ms) / 1e3
             ach = api.algorithmic_flops(v2, c2["n_iters"]) / ks / 1e12
             sweep.append({"config": ci, "workload": c2["name"], "value": float(v2.sum()) * c2["n_iters"] / ks,
-                          "ms_per_step": ks * 1e3, "fp32_tflops": ach, "roofline_frac": ach / fma_peak,
+                          "ms_per_step": ks * 1e3, "steps": sw_steps, "fp32_tflops": ach, "roofline_frac": ach / fma_peak,
+                          "roofline_frac_of_nominal": ach / (SM_COUNT * 128 * 2 * NOMINAL_CLOCK_GHZ / 1e3),
                           "bad_status": int((o2["status"].cpu().numpy() & 3 != 0).sum())})
             del dt2
 
@@ -356,12 +457,94 @@ def run_native(args):
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e2e_ms[0]), "steps": e2e_steps},
             "gpu_launches": args.steps, "roofline": roofline,
-            "objects_flagged": int((status & 3 != 0).sum()), "sweep": sweep}
+            "objects_flagged": int((status & 3 != 0).sum()), "sweep": sweep, "strong": strong,
+            "e2e_call_site": call_site}
+    line["e2e"]["path"] = e2e_path
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline_sequential(scene, tracks, prior, args.cpu_budget)
+        line["cpu_baseline"] = cpu_baseline_config1(args.cpu_budget * 2.5)
+        line["cpu_baseline_headline_config"] = cpu_baseline_sequential(scene, tracks, prior, args.cpu_budget)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling(api, torch, dist, cfg_idx, rank, world, dev, flush):
+    """ONE batch of BASELINE config `cfg_idx`, identical on every rank (seed = config index), sharded by object:
+    contiguous blocks balanced by views -> this rank's block in one persistent launch -> one NCCL all-gather of the
+    final [n, 9] parameters on the same stream.  Timed with CUDA events on that stream, max over ranks; enough steps
+    for >= ~150 ms of timed work."""
+    from odam_b200 import sharding, synthetic
+    c = synthetic.CONFIGS[cfg_idx]
+    scene = synthetic.make_scene(c["n_objects"], c["n_views"], seed=cfg_idx, device=dev)
+    tracks = api.pack_scene(scene)
+    prior = api.prior_table() if c["prior"] else None
+    n_iters = c["n_iters"]
+    parts = sharding.partition_by_views(tracks.view_off, world)
+    lo, hi = parts[rank]
+    dt = api.DeviceTracks(tracks.slice(lo, hi), dev, prior)
+    counts = [h - l for l, h in parts]
+    pad = max(counts)
+    out = api.optimize_device(dt, n_iters=n_iters)
+    buf = torch.zeros((pad, 9), dtype=torch.float32, device=dev)
+    gath = torch.empty((world * pad, 9), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step():
+        api.optimize_device(dt, n_iters=n_iters, out=out)
+        if world > 1:
+            buf[: hi - lo].copy_(out["params"])
+            dist.all_gather_into_tensor(gath, buf)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    units = float(tracks.total_views) * n_iters
+    est_ms = units / (6e8 * world) * 1e3
+    steps = int(min(50, max(3, np.ceil(150.0 / est_ms))))
+    if world > 1:
+        dist.barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    for k in range(steps):
+        flush.zero_()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    tot = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    ms = float(tot[0]) / steps
+    status = out["status"].cpu().numpy()
+    res = {"config": cfg_idx, "workload": f"{c['name']}, {n_iters} iterations, ONE batch sharded by object across {world} GPU(s)",
+           "n_gpus": world, "value": units / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": 3,
+           "objects_per_rank": counts, "scaling": "strong", "all_gather_bytes": int(world * pad * 36) if world > 1 else 0,
+           "fp32_tflops": api.algorithmic_flops(np.diff(tracks.view_off), n_iters) / (ms / 1e3) / 1e12,
+           "bad_status_rank0": int((status & 3 != 0).sum())}
+    del dt, out, buf, gath
+    return res
+
+
+def time_call_site(scene, cfg, device):
+    """tracks -> odam_b200.run_multi_view.optim_process -> result dict, the call OdamProcess.optim_process makes
+    (src/processor.py:352-368): 82-column host tracks in, SuperQuadric objects + oriented boxes out."""
+    from odam_b200 import synthetic
+    from odam_b200.run_multi_view import optim_process
+    seq = synthetic.scene_to_tracks(scene)
+    T_wcs, P_cws = list(seq["T_wcs"]), list(seq["P_cws"])
+    args = (seq["tracks"], seq["img_names"], T_wcs, P_cws, seq["img_h"], seq["img_w"], seq["K"], "super_quadric",
+            bool(cfg["prior"]), cfg["n_iters"], 10)
+    out = optim_process(*args, device=device)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        out = optim_process(*args, device=device)
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.median(ts))
+    units = float(scene.n * scene.V * cfg["n_iters"])
+    return {"value": units / (ms / 1e3), "unit": UNIT, "ms_per_call": ms, "calls": 5, "objects": scene.n, "views": scene.V,
+            "entry": "odam_b200.run_multi_view.optim_process(tracks, img_names, T_wcs, P_cws, h, w, K, 'super_quadric', "
+                     "prior, n_iters, n_views): vectorised staging, H2D, one optimiser launch, D2H, one oriented-box "
+                     "launch, result objects",
+            "returned": sorted(out)}
 
 
 def launch_info(api, tracks):
@@ -397,6 +580,9 @@ def main():
     ap.add_argument("--sweep", type=int, nargs="*", default=[3, 4, 5])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strong", type=int, nargs="*", default=[3, 5], help="configs for the sharded (strong-scaling) measurement")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-call-site", action="store_true")
     ap.add_argument("--clocks", default="smi", choices=["smi", "off"], help="clock sampler (off: diagnostics only)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-iters", type=int, default=20)

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ODAM_SQ_ABI_VERSION 2
+#define ODAM_SQ_ABI_VERSION 3
 #define ODAM_SQ_N_SAMPLES 1000 /* sq_libs.py:545  EqualDistanceSamplerSQ(1000) */
 #define ODAM_SQ_GRID 201       /* _sampler.pyx:423 buffer_size */
 #define ODAM_SQ_N_PARAMS 9
@@ -131,11 +131,38 @@ int odam_sq_project_boxes(const float *params, const int32_t *view_off, const fl
 int odam_sq_project_boxes_host(const float *params, const int32_t *view_off, const float *Ms, int n,
                                float *out_box, int device);
 
+/* compute_ellipsoid_points + compute_oriented_bbox (src/scripts/run_multi_view.py:66-67, src/utils/box_utils.py:319-410):
+ * params[n][9] -> out_corners[n][8][3] DOUBLE, the oriented box of each object's 1000 surface points: min-area rectangle
+ * of the xy convex hull over the directions of the hull edges, upper four corners (z_max) first, then the same four at
+ * z_min.  The reference takes its hull from scipy/Qhull and skips the hull's closing edge; the kernel builds the hull
+ * itself (gift wrapping, exact orientation tests) and reproduces Qhull's vertex order (see csrc/sq_postproc.cuh).
+ * out_flag[n] (may be NULL): 0 = ok, bit 0 = Qhull's vertex order could not be predicted with certainty (degenerate
+ * extreme points), bit 1 = fewer than 3 hull vertices.  out_xyz (may be NULL): the surface points [n][1000][3] float. */
+int odam_sq_oriented_boxes(const float *params, int n, double *out_corners, int32_t *out_flag, float *out_xyz,
+                           void *stream);
+int odam_sq_oriented_boxes_host(const float *params, int n, double *out_corners, int32_t *out_flag, float *out_xyz,
+                                int device);
+/* compute_oriented_bbox of arbitrary point sets: points[n][n_pts][3] float32 (n_pts <= 1024), HOST pointers. */
+int odam_sq_oriented_boxes_of_points_host(const float *points, int n, int n_pts, double *out_corners,
+                                          int32_t *out_flag, int device);
+
+/* The pair costs of merge_process (src/scripts/run_merge.py:79-122) between the two optimisation passes:
+ * boxes[n][8][3] double (bboxes_qc), cls[n] class ids (NULL = every pair may merge) ->
+ * out_cost[n][n] = 1 - box3d_iou(box_i, box_j)[0] (src/utils/box_utils.py:97-120) where the classes allow a merge (equal,
+ * or both in {4, 5}), else 1; symmetric, zero diagonal -- i.e. cost_mat after `cost_mat += cost_mat.T`.
+ * out_iou3d / out_iou2d [n][n] (any may be NULL): the raw IoU values for i < j.  HOST pointers; one thread per pair.
+ * Identical or edge-sharing rectangles make the reference's clipper divide by zero and raise; here such a pair
+ * yields NaN. */
+int odam_sq_merge_cost_host(const double *boxes, const int32_t *cls, int n, double *out_cost, double *out_iou3d,
+                            double *out_iou2d, int device);
+
 /* Drop-in for the reference's own native entry point, fast_sampler/sampling.hpp:5-15
  *   void sample_on_batch(float *shapes, float *epsilons, float *etas, float *omegas, int B, int M, int N,
  *                        int buffer_size, int seed)
  * as bound by _sampler.pyx:413-441 (N = 1000, buffer_size = 201, seed = 0 are the only values that path uses;
- * anything else is ODAM_SQ_ERR_ARG).  shapes[B][M][3], epsilons[B][M][2] -> etas, omegas [B][M][N]; HOST pointers. */
+ * anything else is ODAM_SQ_ERR_ARG).  shapes[B][M][3], epsilons[B][M][2] -> etas, omegas [B][M][N]; HOST pointers.
+ * As in the reference, ONE generator is seeded per call and keeps drawing across the B*M primitives
+ * (sampling.cpp:169-214): primitive p sees uniforms [2000p, 2000p + 2000) of mt19937(seed). */
 int odam_sq_sample_on_batch_host(const float *shapes, const float *epsilons, float *etas, float *omegas,
                                  int B, int M, int N, int buffer_size, int seed, int device);
 

@@ -16,7 +16,8 @@ N_SAMPLES, GRID = 1000, 201
 EXPORTS = ("odam_sq_abi_version", "odam_sq_error_string", "odam_sq_last_cuda_error", "odam_sq_init",
            "odam_sq_optimize", "odam_sq_optimize_host", "odam_sq_sample_points", "odam_sq_sample_points_host",
            "odam_sq_project_boxes", "odam_sq_project_boxes_host", "odam_sq_query_launch",
-           "odam_sq_sample_on_batch_host", "odam_sq_fma_peak", "odam_sq_selftest")
+           "odam_sq_sample_on_batch_host", "odam_sq_fma_peak", "odam_sq_selftest", "odam_sq_oriented_boxes",
+           "odam_sq_oriented_boxes_host", "odam_sq_oriented_boxes_of_points_host", "odam_sq_merge_cost_host")
 
 
 class Options(C.Structure):
@@ -57,6 +58,10 @@ def load():
         L.odam_sq_project_boxes.argtypes = [vp, vp, vp, ci, vp, vp]
         L.odam_sq_project_boxes_host.argtypes = [vp, vp, vp, ci, vp, ci]
         L.odam_sq_sample_on_batch_host.argtypes = [vp] * 4 + [ci] * 6
+        L.odam_sq_oriented_boxes.argtypes = [vp, ci, vp, vp, vp, vp]
+        L.odam_sq_oriented_boxes_host.argtypes = [vp, ci, vp, vp, vp, ci]
+        L.odam_sq_oriented_boxes_of_points_host.argtypes = [vp, ci, ci, vp, vp, ci]
+        L.odam_sq_merge_cost_host.argtypes = [vp, vp, ci, vp, vp, vp, ci]
         L.odam_sq_fma_peak.argtypes = [ci, C.POINTER(C.c_double)]
         L.odam_sq_selftest.argtypes = [ci, C.c_uint32, C.c_longlong, C.POINTER(C.c_longlong)]
         L.odam_sq_query_launch.argtypes = [vp, ci, C.POINTER(Options)] + [C.POINTER(ci)] * 6

@@ -211,6 +211,47 @@ def project_boxes_host(params, view_off, Ms, device=0):
     return out
 
 
+def oriented_boxes_host(params, device=0, want_points=False):
+    """compute_ellipsoid_points + compute_oriented_bbox for [n,9] parameter rows in ONE launch (odam_sq_oriented_boxes_host):
+    returns corners [n,8,3] float64 (upper four first), flags [n] int32 and, when asked, the points [n,1000,3] float32."""
+    L = _lib.load()
+    p = np.ascontiguousarray(params, np.float32).reshape(-1, 9)
+    n = p.shape[0]
+    corners = np.zeros((n, 8, 3), np.float64)
+    flags = np.zeros(n, np.int32)
+    pts = np.zeros((n, _lib.N_SAMPLES, 3), np.float32) if want_points else None
+    _lib.check(L.odam_sq_oriented_boxes_host(_lib.ptr(p), n, _lib.ptr(corners), _lib.ptr(flags), _lib.ptr(pts), device))
+    return (corners, flags, pts) if want_points else (corners, flags)
+
+
+def oriented_boxes_of_points_host(points, device=0):
+    """compute_oriented_bbox (reference box_utils.py:319-410) of point sets [n, n_pts, 3] (n_pts <= 1024)."""
+    L = _lib.load()
+    pts = np.ascontiguousarray(points, np.float32)
+    if pts.ndim == 2:
+        pts = pts[None]
+    n, n_pts = pts.shape[0], pts.shape[1]
+    corners = np.zeros((n, 8, 3), np.float64)
+    flags = np.zeros(n, np.int32)
+    _lib.check(L.odam_sq_oriented_boxes_of_points_host(_lib.ptr(pts), n, n_pts, _lib.ptr(corners), _lib.ptr(flags), device))
+    return corners, flags
+
+
+def merge_cost_host(boxes, cls=None, device=0, want_iou=False):
+    """The cost matrix of merge_process (reference run_merge.py:90-121): boxes [n,8,3] float64 (bboxes_qc), cls [n] class
+    ids or None -> cost [n,n] float64 (1 - IoU3D where the classes allow a merge, else 1; symmetric, zero diagonal).
+    want_iou: also the raw (iou3d, iou2d) matrices for i < j."""
+    L = _lib.load()
+    b = np.ascontiguousarray(boxes, np.float64).reshape(-1, 8, 3)
+    n = b.shape[0]
+    c = None if cls is None else np.ascontiguousarray(cls, np.int32).reshape(n)
+    cost = np.zeros((n, n), np.float64)
+    i3 = np.zeros((n, n), np.float64) if want_iou else None
+    i2 = np.zeros((n, n), np.float64) if want_iou else None
+    _lib.check(L.odam_sq_merge_cost_host(_lib.ptr(b), _lib.ptr(c), n, _lib.ptr(cost), _lib.ptr(i3), _lib.ptr(i2), device))
+    return (cost, i3, i2) if want_iou else cost
+
+
 class DeviceTracks:
     """PackedTracks resident in HBM as torch tensors (plumbing only: allocation + stream)."""
 
@@ -243,7 +284,10 @@ def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr
         threads, cluster, code_layout, max_slices = q["threads"], q["cluster"], q["code_layout"], q["max_slices"]
     o.threads, o.max_slices, o.cluster, o.code_layout = int(threads), int(max_slices), int(cluster), int(code_layout)
     o.max_views = int(np.diff(dt.view_off_host).max()) if dt.n else 0
-    if cycles is not None:  # int64 CUDA tensor [n, 8]: per-phase SM cycles (diagnostics)
+    if cycles is not None:  # int64 CUDA tensor [n, 16]: per-phase SM cycles (diagnostics; slot names in tools/prof_run.py)
+        if tuple(cycles.shape) != (dt.n, 16) or cycles.dtype != torch.int64 or not cycles.is_contiguous() \
+                or cycles.device != dt.device:
+            raise ValueError("cycles must be a contiguous int64 CUDA tensor of shape [n, 16] on the tracks' device")
         o.out_cycles = cycles.data_ptr()
     p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
     with torch.cuda.device(dt.device):

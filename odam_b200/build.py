@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "sq_kernels.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", "sq_device.cuh"), os.path.join(HERE, "csrc", "sq_math.cuh"), os.path.join(HERE, "..", "include", "odam_sq.h")]
+DEPS = SRC + [os.path.join(HERE, "csrc", "sq_device.cuh"), os.path.join(HERE, "csrc", "sq_math.cuh"), os.path.join(HERE, "csrc", "sq_glibc_data.h"), os.path.join(HERE, "..", "include", "odam_sq.h")]
 OUT = os.path.join(HERE, "lib", "libodam_sq.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared"]

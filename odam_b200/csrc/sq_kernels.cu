@@ -29,6 +29,7 @@
 #define SQ_FFMA2 1   // phase E on packed fp32 pairs (FFMA2/FMUL2); 0 = scalar FFMA build for A/B timing
 #endif
 #include "sq_device.cuh"
+#include "sq_postproc.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
         S.par[tid] = A.init[(size_t)obj * 9 + tid];
         S.m[tid] = A.m0 ? A.m0[(size_t)obj * 9 + tid] : 0.f;
         S.v[tid] = A.v0 ? A.v0[(size_t)obj * 9 + tid] : 0.f;
-        if (A.prior) S.prior[tid] = A.prior[(size_t)A.cls[obj] * 9 + tid];
+        if (A.prior) S.prior[tid] = A.prior[(size_t)min(max(A.cls[obj], 0), 7) * 9 + tid];  // host entry validates; device entry clamps
     }
     if (tid < 3) S.s0[tid] = A.s0 ? A.s0[(size_t)obj * 3 + tid] : A.init[(size_t)obj * 9 + 4 + tid];
     if (tid == 0) {
@@ -664,7 +665,10 @@ __global__ void __launch_bounds__(256) sq_points_kernel(const float *params, int
 
 // The reference's own native entry point (sampling.hpp:5-15 sample_on_batch, B*M primitives, N=1000,
 // buffer_size=201, seed=0): a[n][3], e[n][2] -> etas[n][1000], omegas[n][1000].  One CTA (2 warps) per primitive.
-__global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const float *e, int n, float *etas, float *omegas)
+// u_eta / k_omega: per-primitive draws [n][1000] of ONE generator that keeps drawing across the primitives of a call
+// (sampling.cpp:169-214: primitive p consumes uniforms 2000p .. 2000p+1999), or NULL = the tables of primitive 0.
+__global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const float *e, int n, float *etas, float *omegas,
+                                                       const float *u_eta, const uint8_t *k_omega)
 {
     __shared__ Smem S;
     extern __shared__ __align__(16) unsigned char scratch_raw[];
@@ -687,8 +691,81 @@ __global__ void __launch_bounds__(64) sq_angles_kernel(const float *a, const flo
     }
     __syncthreads();
     for (int i = tid; i < kN; i += blockDim.x) {
-        etas[(size_t)obj * kN + i] = S.ge.slot[lower_bound_201(S.cdf, g_u_eta[i])].x;
-        omegas[(size_t)obj * kN + i] = S.go.slot[g_k_omega[i]].x;
+        const float uu = u_eta ? u_eta[(size_t)obj * kN + i] : g_u_eta[i];
+        const int ko = k_omega ? k_omega[(size_t)obj * kN + i] : g_k_omega[i];
+        etas[(size_t)obj * kN + i] = S.ge.slot[lower_bound_201(S.cdf, uu)].x;
+        omegas[(size_t)obj * kN + i] = S.go.slot[ko].x;
+    }
+}
+
+// compute_ellipsoid_points + compute_oriented_bbox (run_multi_view.py:66-67): params -> the 8 corners of the oriented
+// box of the 1000 surface points (float64, upper four first), one CTA per object; optionally the points themselves.
+__global__ void __launch_bounds__(256) sq_obb_kernel(const float *params, int n, double *out_corners, int32_t *out_flag,
+                                                      float *out_xyz)
+{
+    __shared__ Smem S;
+    __shared__ HullScratch H;
+    extern __shared__ __align__(16) unsigned char scratch_raw[];
+    const int tid = threadIdx.x, obj = blockIdx.x;
+    if (tid < 9) S.par[tid] = params[(size_t)obj * 9 + tid];
+    if (tid == 0) {
+        const float pi = 3.14159274101257324f, pi_2 = __fmul_rn(pi, 0.5f);
+        pool_init(S.ge, pi_2, -pi_2);
+        pool_init(S.go, pi, -pi);
+    }
+    __syncthreads();
+    if (tid < 10) derive_param(S, tid);
+    __syncthreads();
+    sample_surface<true>(S, reinterpret_cast<GridSpec *>(scratch_raw), tid, blockDim.x, false);
+    if (out_xyz)
+        for (int i = tid; i < kN; i += blockDim.x) {
+            float *o = out_xyz + ((size_t)obj * kN + i) * 3;
+            o[0] = S.px[i]; o[1] = S.py[i]; o[2] = S.pz[i];
+        }
+    obb_of_points(H, S.px, S.py, S.pz, kN, out_corners + (size_t)obj * 24, out_flag ? out_flag + obj : nullptr);
+}
+
+// compute_oriented_bbox of arbitrary point sets: pts[n][n_pts][3] float32, n_pts <= 1024
+__global__ void __launch_bounds__(256) sq_obb_points_kernel(const float *pts, int n, int n_pts, double *out_corners,
+                                                             int32_t *out_flag)
+{
+    __shared__ float px[kHullMax], py[kHullMax], pz[kHullMax];
+    __shared__ HullScratch H;
+    const int obj = blockIdx.x;
+    for (int i = threadIdx.x; i < n_pts; i += blockDim.x) {
+        const float *p = pts + ((size_t)obj * n_pts + i) * 3;
+        px[i] = p[0]; py[i] = p[1]; pz[i] = p[2];
+    }
+    __syncthreads();
+    obb_of_points(H, px, py, pz, n_pts, out_corners + (size_t)obj * 24, out_flag ? out_flag + obj : nullptr);
+}
+
+// merge_process's pair costs (run_merge.py:90-121): cost[i][j] = 1 - box3d_iou(box_i, box_j)[0] when the classes allow
+// a merge (equal, or both in {4, 5}), else 1; symmetric, zero diagonal.  One thread per pair i < j.
+// cls == NULL: every pair is evaluated.  iou3d / iou2d (optional, [n][n]): the raw values for i < j, zero elsewhere.
+__global__ void sq_merge_cost_kernel(const double *boxes, const int32_t *cls, int n, double *cost, double *iou3d, double *iou2d)
+{
+    const long long total = (long long)n * n;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / n), j = (int)(t - (long long)i * n);
+        if (i > j) continue;
+        if (i == j) {
+            if (cost) cost[t] = 0.0;
+            if (iou3d) iou3d[t] = 0.0;
+            if (iou2d) iou2d[t] = 0.0;
+            continue;
+        }
+        bool mergable = true;
+        if (cls) {
+            const int a = cls[i], b = cls[j];
+            mergable = a == b || ((a == 4 || a == 5) && (b == 4 || b == 5));
+        }
+        double v3 = 0.0, v2 = 0.0;
+        if (mergable) box3d_iou_pair(boxes + (size_t)i * 24, boxes + (size_t)j * 24, &v3, &v2);
+        const double c = mergable ? 1.0 - v3 : 1.0;
+        if (cost) { cost[t] = c; cost[(size_t)j * n + i] = c; }
+        if (iou3d) { iou3d[t] = v3; iou3d[(size_t)j * n + i] = 0.0; }
+        if (iou2d) { iou2d[t] = v2; iou2d[(size_t)j * n + i] = 0.0; }
     }
 }
 
@@ -817,16 +894,32 @@ static void gen_logtab(float ta, float tb, int pos, std::vector<double2> &tab)
     gen_logtab(th, tb, 2 * pos + 1, tab);
 }
 
+// restores the caller's current device on every return path of the *_host entry points
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t enter(int device)
+    {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) { prev = -1; return e; }
+        return cudaSetDevice(device);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct AdamTab {   // bias-correction table of one (stream, schedule): kept until evicted, never shared across streams
+    cudaStream_t stream; int iters, step0; double lr, lrs; float *dev; int cap;
+};
+
 struct DeviceState {
     bool ready = false;
+    std::mutex host_mu;   // one *_host call at a time per device: they share the staging workspace and the stream
+    std::vector<AdamTab> tabs;
     int sm_count = 0;
     int max_smem_optin = 0;
     // workspace of the *_host entry points
     cudaStream_t stream = nullptr;
     void *dbuf = nullptr; size_t dbytes = 0;
     void *hbuf = nullptr; size_t hbytes = 0;   // pinned staging
-    float *adam_tab = nullptr; int adam_cap = 0;
-    std::vector<float> adam_host; int adam_iters = -1, adam_step0 = -1; double adam_lr = 0, adam_lrs = 0;
 };
 static DeviceState g_dev[64];
 static std::mutex g_mu;
@@ -848,12 +941,11 @@ static int ensure_init(int device)
     std::lock_guard<std::mutex> lk(g_mu);
     DeviceState &D = g_dev[device];
     if (D.ready) return ODAM_SQ_OK;
-    int cur = 0;
-    CU(cudaGetDevice(&cur));
-    CU(cudaSetDevice(device));
+    DeviceGuard guard;
+    CU(guard.enter(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) { cudaSetDevice(cur); return ODAM_SQ_ERR_DEVICE; }
+    if (prop.major != 10) return ODAM_SQ_ERR_DEVICE;
     D.sm_count = prop.multiProcessorCount;
     D.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     std::vector<float> u(2 * kN);
@@ -881,8 +973,8 @@ static int ensure_init(int device)
     CU(cudaFuncSetAttribute(sq_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaFuncSetAttribute(sq_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaFuncSetAttribute(sq_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
+    CU(cudaFuncSetAttribute(sq_obb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
-    CU(cudaSetDevice(cur));
     D.ready = true;
     return ODAM_SQ_OK;
 }
@@ -1031,7 +1123,17 @@ int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *
     int maxv = 0;
     for (int i = 0; i < n; i++) maxv = std::max(maxv, view_off[i + 1] - view_off[i]);
     LaunchCfg L;
-    int rc = choose_launch(maxv, (double)(view_off[n] - view_off[0]) / n, n, opt, 148, 232448, L);
+    int sm_count = 148, smem_optin = 232448;   // B200; the current device's own numbers once it is initialised
+    {
+        int dev = -1;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_dev[dev].ready) {
+            sm_count = g_dev[dev].sm_count;
+            smem_optin = g_dev[dev].max_smem_optin;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    int rc = choose_launch(maxv, (double)(view_off[n] - view_off[0]) / n, n, opt, sm_count, smem_optin, L);
     if (rc) return rc;
     if (threads) *threads = L.threads;
     if (cluster) *cluster = L.cluster;
@@ -1077,29 +1179,44 @@ int odam_sq_optimize(const float *init, const int32_t *cls, const int32_t *view_
     LaunchCfg L;
     rc = choose_launch(maxv, meanv, n, opt, D.sm_count, D.max_smem_optin, L);
     if (rc) return rc;
-    // Adam bias-correction table (host doubles, as torch computes them in Python floats); cached per device
+    // Adam bias-correction table (host doubles, as torch computes them in Python floats); one cached table per
+    // (stream, schedule), so launches on different streams never share -- or overwrite -- each other's table
+    const float *adam_dev = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        int step0 = opt ? opt->step0 : 0;
-        if (D.adam_iters != n_iters || D.adam_step0 != step0 || D.adam_lr != (double)lr || D.adam_lrs != (double)lr_shape) {
-            CU(cudaStreamSynchronize(st));  // a previous launch may still read the old table
-            if (D.adam_cap < n_iters) {
-                if (D.adam_tab) cudaFree(D.adam_tab);
-                D.adam_tab = nullptr;
-                CU(cudaMalloc(&D.adam_tab, sizeof(float) * 4 * n_iters));
-                D.adam_cap = n_iters;
+        const int step0 = opt ? opt->step0 : 0;
+        for (const AdamTab &t : D.tabs)
+            if (t.stream == st && t.iters == n_iters && t.step0 == step0 && t.lr == (double)lr && t.lrs == (double)lr_shape)
+                adam_dev = t.dev;
+        if (!adam_dev) {
+            AdamTab *slot = nullptr;
+            for (AdamTab &t : D.tabs)
+                if (t.stream == st) slot = &t;                    // this stream's previous schedule: reuse its buffer
+            if (!slot && D.tabs.size() >= 16) slot = &D.tabs[0];  // bounded cache: recycle the oldest entry
+            if (slot) {
+                CU(cudaStreamSynchronize(slot->stream));          // its last launch may still read the table
+                if (slot->cap < n_iters) { cudaFree(slot->dev); slot->dev = nullptr; slot->cap = 0; }
+            } else {
+                D.tabs.push_back(AdamTab{st, 0, 0, 0, 0, nullptr, 0});
+                slot = &D.tabs.back();
             }
-            fill_adam_tab(D.adam_host, n_iters, step0, (double)lr, (double)lr_shape);
-            CU(cudaMemcpyAsync(D.adam_tab, D.adam_host.data(), sizeof(float) * D.adam_host.size(),
-                               cudaMemcpyHostToDevice, st));
-            D.adam_iters = n_iters; D.adam_step0 = step0; D.adam_lr = (double)lr; D.adam_lrs = (double)lr_shape;
+            if (!slot->dev) {
+                CU(cudaMalloc(&slot->dev, sizeof(float) * 4 * n_iters));
+                slot->cap = n_iters;
+            }
+            std::vector<float> tab;
+            fill_adam_tab(tab, n_iters, step0, (double)lr, (double)lr_shape);
+            // pageable source: the copy has left the host vector when the call returns
+            CU(cudaMemcpyAsync(slot->dev, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, st));
+            slot->stream = st; slot->iters = n_iters; slot->step0 = step0; slot->lr = (double)lr; slot->lrs = (double)lr_shape;
+            adam_dev = slot->dev;
         }
     }
     OptArgs A;
     memset(&A, 0, sizeof A);
     A.init = init; A.cls = cls; A.view_off = view_off; A.Ms = Ms; A.box = box; A.mask = mask; A.prior = prior;
     A.n = n; A.n_iters = n_iters; A.optimize_shapes = representation == ODAM_SQ_REPR_SUPER_QUADRIC;
-    A.adam_tab = D.adam_tab;
+    A.adam_tab = adam_dev;
     A.out_params = out_params; A.out_loss = out_loss; A.out_status = out_status;
     if (opt) {
         A.m0 = opt->m0; A.v0 = opt->v0; A.s0 = opt->s0;
@@ -1156,16 +1273,19 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
         maxv = std::max(maxv, view_off[i + 1] - view_off[i]);
     }
     if (view_off[0] != 0) return ODAM_SQ_ERR_ARG;
+    if (prior)
+        for (int i = 0; i < n; i++)
+            if (cls[i] < 0 || cls[i] > 7) return ODAM_SQ_ERR_ARG;   // 8 classes (sq_libs.py:13-22)
     const size_t SV = (size_t)view_off[n];
     int rc = ensure_init(device);
     if (rc) return rc;
     DeviceState &D = g_dev[device];
-    int cur = 0;
-    CU(cudaGetDevice(&cur));
-    CU(cudaSetDevice(device));
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
     LaunchCfg L;
     rc = choose_launch(maxv, (double)SV / n, n, opt, D.sm_count, D.max_smem_optin, L);
-    if (rc) { cudaSetDevice(cur); return rc; }
+    if (rc) return rc;
 
     // one packed staging buffer: inputs first, outputs after; same layout on host (pinned) and device
     size_t in_bytes = 0, total = 0;
@@ -1194,7 +1314,7 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
         std::lock_guard<std::mutex> lk(g_mu);
         rc = ensure_ws(D, total);
     }
-    if (rc) { cudaSetDevice(cur); return rc; }
+    if (rc) return rc;
     unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
     memcpy(h + o_init, init, sizeof(float) * 9 * n);
     if (cls) memcpy(h + o_cls, cls, sizeof(int32_t) * n);
@@ -1232,7 +1352,7 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
         A.out_param_hist = opt->out_param_hist ? (float *)(d + o_hist) : nullptr;
     }
     rc = launch_optimize(D, A, L, st);
-    if (rc) { cudaSetDevice(cur); return rc; }
+    if (rc) return rc;
     CU(cudaMemcpyAsync(h + in_bytes, d + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(out_params, h + o_par, sizeof(float) * 9 * n);
@@ -1248,7 +1368,6 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
         if (opt->out_grids) memcpy(opt->out_grids, h + o_grids, sizeof(float) * 2 * kG * n);
         if (opt->out_param_hist) memcpy(opt->out_param_hist, h + o_hist, sizeof(float) * 9 * (size_t)n * n_iters);
     }
-    CU(cudaSetDevice(cur));
     return ODAM_SQ_OK;
 }
 
@@ -1259,12 +1378,12 @@ int odam_sq_sample_points_host(const float *params, int n, float *out_xyz, int d
     int rc = ensure_init(device);
     if (rc) return rc;
     DeviceState &D = g_dev[device];
-    int cur = 0;
-    CU(cudaGetDevice(&cur));
-    CU(cudaSetDevice(device));
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
     size_t in_b = ((sizeof(float) * 9 * n + 255) / 256) * 256, out_b = sizeof(float) * 3 * kN * (size_t)n;
     { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, in_b + out_b); }
-    if (rc) { cudaSetDevice(cur); return rc; }
+    if (rc) return rc;
     unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
     memcpy(h, params, sizeof(float) * 9 * n);
     CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
@@ -1273,7 +1392,6 @@ int odam_sq_sample_points_host(const float *params, int n, float *out_xyz, int d
     CU(cudaMemcpyAsync(h + in_b, d + in_b, out_b, cudaMemcpyDeviceToHost, D.stream));
     CU(cudaStreamSynchronize(D.stream));
     memcpy(out_xyz, h + in_b, out_b);
-    CU(cudaSetDevice(cur));
     return ODAM_SQ_OK;
 }
 
@@ -1285,16 +1403,16 @@ int odam_sq_project_boxes_host(const float *params, const int32_t *view_off, con
     int rc = ensure_init(device);
     if (rc) return rc;
     DeviceState &D = g_dev[device];
-    int cur = 0;
-    CU(cudaGetDevice(&cur));
-    CU(cudaSetDevice(device));
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
     const size_t SV = (size_t)view_off[n];
     Carver C;
     size_t o_p = C.take<float>((size_t)n * 9), o_v = C.take<int32_t>(n + 1), o_M = C.take<float>(SV * 12);
     size_t in_b = (C.off + 255) & ~(size_t)255;
     size_t out_b = sizeof(float) * 4 * SV;
     { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, in_b + out_b); }
-    if (rc) { cudaSetDevice(cur); return rc; }
+    if (rc) return rc;
     unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
     memcpy(h + o_p, params, sizeof(float) * 9 * n);
     memcpy(h + o_v, view_off, sizeof(int32_t) * (n + 1));
@@ -1306,7 +1424,121 @@ int odam_sq_project_boxes_host(const float *params, const int32_t *view_off, con
     CU(cudaMemcpyAsync(h + in_b, d + in_b, out_b, cudaMemcpyDeviceToHost, D.stream));
     CU(cudaStreamSynchronize(D.stream));
     memcpy(out_box, h + in_b, out_b);
-    CU(cudaSetDevice(cur));
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_oriented_boxes_host(const float *params, int n, double *out_corners, int32_t *out_flag, float *out_xyz,
+                                int device)
+{
+    if (!params || !out_corners || n < 0) return ODAM_SQ_ERR_ARG;
+    if (n == 0) return ODAM_SQ_OK;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
+    Carver C;
+    size_t o_p = C.take<float>((size_t)n * 9);
+    size_t in_b = (C.off + 255) & ~(size_t)255;
+    C.off = in_b;
+    size_t o_c = C.take<double>((size_t)n * 24), o_f = C.take<int32_t>(n);
+    size_t o_x = C.take<float>(out_xyz ? (size_t)n * kN * 3 : 0);
+    rc = ensure_ws(D, C.off);
+    if (rc) return rc;
+    unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
+    memcpy(h + o_p, params, sizeof(float) * 9 * n);
+    CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
+    sq_obb_kernel<<<n, 256, kFwdSmem, D.stream>>>((float *)(d + o_p), n, (double *)(d + o_c), (int32_t *)(d + o_f),
+                                                      out_xyz ? (float *)(d + o_x) : nullptr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h + in_b, d + in_b, C.off - in_b, cudaMemcpyDeviceToHost, D.stream));
+    CU(cudaStreamSynchronize(D.stream));
+    memcpy(out_corners, h + o_c, sizeof(double) * 24 * n);
+    if (out_flag) memcpy(out_flag, h + o_f, sizeof(int32_t) * n);
+    if (out_xyz) memcpy(out_xyz, h + o_x, sizeof(float) * 3 * kN * (size_t)n);
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_oriented_boxes(const float *params, int n, double *out_corners, int32_t *out_flag, float *out_xyz,
+                           void *stream)
+{
+    if (!params || !out_corners || n < 0) return ODAM_SQ_ERR_ARG;
+    if (n == 0) return ODAM_SQ_OK;
+    int device = 0;
+    CU(cudaGetDevice(&device));
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    sq_obb_kernel<<<n, 256, kFwdSmem, (cudaStream_t)stream>>>(params, n, out_corners, out_flag, out_xyz);
+    CU(cudaGetLastError());
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_oriented_boxes_of_points_host(const float *points, int n, int n_pts, double *out_corners, int32_t *out_flag,
+                                          int device)
+{
+    if (!points || !out_corners || n < 0 || n_pts < 1 || n_pts > kHullMax) return ODAM_SQ_ERR_ARG;
+    if (n == 0) return ODAM_SQ_OK;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
+    Carver C;
+    size_t o_p = C.take<float>((size_t)n * n_pts * 3);
+    size_t in_b = (C.off + 255) & ~(size_t)255;
+    C.off = in_b;
+    size_t o_c = C.take<double>((size_t)n * 24), o_f = C.take<int32_t>(n);
+    rc = ensure_ws(D, C.off);
+    if (rc) return rc;
+    unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
+    memcpy(h + o_p, points, sizeof(float) * 3 * (size_t)n * n_pts);
+    CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
+    sq_obb_points_kernel<<<n, 256, 0, D.stream>>>((float *)(d + o_p), n, n_pts, (double *)(d + o_c), (int32_t *)(d + o_f));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h + in_b, d + in_b, C.off - in_b, cudaMemcpyDeviceToHost, D.stream));
+    CU(cudaStreamSynchronize(D.stream));
+    memcpy(out_corners, h + o_c, sizeof(double) * 24 * n);
+    if (out_flag) memcpy(out_flag, h + o_f, sizeof(int32_t) * n);
+    return ODAM_SQ_OK;
+}
+
+int odam_sq_merge_cost_host(const double *boxes, const int32_t *cls, int n, double *out_cost, double *out_iou3d,
+                            double *out_iou2d, int device)
+{
+    if (!boxes || n < 0 || !(out_cost || out_iou3d || out_iou2d)) return ODAM_SQ_ERR_ARG;
+    if (n == 0) return ODAM_SQ_OK;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    DeviceState &D = g_dev[device];
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
+    const size_t nn = (size_t)n * n;
+    Carver C;
+    size_t o_b = C.take<double>((size_t)n * 24), o_cls = C.take<int32_t>(cls ? n : 0);
+    size_t in_b = (C.off + 255) & ~(size_t)255;
+    C.off = in_b;
+    size_t o_c = C.take<double>(out_cost ? nn : 0), o_3 = C.take<double>(out_iou3d ? nn : 0), o_2 = C.take<double>(out_iou2d ? nn : 0);
+    rc = ensure_ws(D, C.off);
+    if (rc) return rc;
+    unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
+    memcpy(h + o_b, boxes, sizeof(double) * 24 * n);
+    if (cls) memcpy(h + o_cls, cls, sizeof(int32_t) * n);
+    CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
+    const int threads = 128;
+    const int blocks = (int)std::min<size_t>((nn + threads - 1) / threads, (size_t)D.sm_count * 16);
+    sq_merge_cost_kernel<<<blocks, threads, 0, D.stream>>>((double *)(d + o_b), cls ? (int32_t *)(d + o_cls) : nullptr, n,
+                                                           out_cost ? (double *)(d + o_c) : nullptr,
+                                                           out_iou3d ? (double *)(d + o_3) : nullptr,
+                                                           out_iou2d ? (double *)(d + o_2) : nullptr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h + in_b, d + in_b, C.off - in_b, cudaMemcpyDeviceToHost, D.stream));
+    CU(cudaStreamSynchronize(D.stream));
+    if (out_cost) memcpy(out_cost, h + o_c, sizeof(double) * nn);
+    if (out_iou3d) memcpy(out_iou3d, h + o_3, sizeof(double) * nn);
+    if (out_iou2d) memcpy(out_iou2d, h + o_2, sizeof(double) * nn);
     return ODAM_SQ_OK;
 }
 
@@ -1320,28 +1552,43 @@ int odam_sq_sample_on_batch_host(const float *shapes, const float *epsilons, flo
     int rc = ensure_init(device);
     if (rc) return rc;
     DeviceState &D = g_dev[device];
-    int cur = 0;
-    CU(cudaGetDevice(&cur));
-    CU(cudaSetDevice(device));
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
     Carver C;
     size_t o_a = C.take<float>((size_t)n * 3), o_e = C.take<float>((size_t)n * 2);
+    // one generator per CALL, drawing on across the primitives (sampling.cpp:169): primitive p uses uniforms
+    // [2000p, 2000p+1000) for its etas and [2000p+1000, 2000p+2000) for its omega indices
+    const bool many = n > 1;
+    size_t o_u = C.take<float>(many ? (size_t)n * kN : 0), o_k = C.take<uint8_t>(many ? (size_t)n * kN : 0);
     size_t in_b = (C.off + 255) & ~(size_t)255;
     C.off = in_b;
     size_t o_eta = C.take<float>((size_t)n * kN), o_om = C.take<float>((size_t)n * kN);
     { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, C.off); }
-    if (rc) { cudaSetDevice(cur); return rc; }
+    if (rc) return rc;
     unsigned char *h = (unsigned char *)D.hbuf, *d = (unsigned char *)D.dbuf;
     memcpy(h + o_a, shapes, sizeof(float) * 3 * n);
     memcpy(h + o_e, epsilons, sizeof(float) * 2 * n);
+    if (many) {
+        std::vector<float> u((size_t)2 * kN * n);
+        host_uniforms(0u, 2 * kN * n, u.data());
+        float *hu = (float *)(h + o_u);
+        uint8_t *hk = h + o_k;
+        for (int p = 0; p < n; p++)
+            for (int i = 0; i < kN; i++) {
+                hu[(size_t)p * kN + i] = u[(size_t)2 * kN * p + i];
+                hk[(size_t)p * kN + i] = (uint8_t)(int)(u[(size_t)2 * kN * p + kN + i] * (float)kG);  // sampling.cpp:211
+            }
+    }
     CU(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, D.stream));
     sq_angles_kernel<<<n, 64, kFwdSmem, D.stream>>>((float *)(d + o_a), (float *)(d + o_e), n, (float *)(d + o_eta),
-                                                         (float *)(d + o_om));
+                                                         (float *)(d + o_om), many ? (float *)(d + o_u) : nullptr,
+                                                         many ? d + o_k : nullptr);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h + in_b, d + in_b, C.off - in_b, cudaMemcpyDeviceToHost, D.stream));
     CU(cudaStreamSynchronize(D.stream));
     memcpy(etas, h + o_eta, sizeof(float) * kN * (size_t)n);
     memcpy(omegas, h + o_om, sizeof(float) * kN * (size_t)n);
-    CU(cudaSetDevice(cur));
     return ODAM_SQ_OK;
 }
 
@@ -1351,11 +1598,11 @@ int odam_sq_fma_peak(int device, double *tflops)
     int rc = ensure_init(device);
     if (rc) return rc;
     DeviceState &D = g_dev[device];
-    int cur = 0;
-    CU(cudaGetDevice(&cur));
-    CU(cudaSetDevice(device));
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
     { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, 4096); }
-    if (rc) { cudaSetDevice(cur); return rc; }
+    if (rc) return rc;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
@@ -1374,7 +1621,6 @@ int odam_sq_fma_peak(int device, double *tflops)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *tflops = best;
-    CU(cudaSetDevice(cur));
     return ODAM_SQ_OK;
 }
 
@@ -1384,18 +1630,17 @@ int odam_sq_selftest(int device, uint32_t seed, long long n, long long *mismatch
     int rc = ensure_init(device);
     if (rc) return rc;
     DeviceState &D = g_dev[device];
-    int cur = 0;
-    CU(cudaGetDevice(&cur));
-    CU(cudaSetDevice(device));
+    DeviceGuard guard;
+    CU(guard.enter(device));
+    std::lock_guard<std::mutex> host_lock(D.host_mu);
     { std::lock_guard<std::mutex> lk(g_mu); rc = ensure_ws(D, 4096); }
-    if (rc) { cudaSetDevice(cur); return rc; }
+    if (rc) return rc;
     CU(cudaMemsetAsync(D.dbuf, 0, 8, D.stream));
     div_selftest_kernel<<<D.sm_count * 4, 256, 0, D.stream>>>(seed, n, (unsigned long long *)D.dbuf);
     unsigned long long h = 0;
     CU(cudaMemcpyAsync(&h, D.dbuf, 8, cudaMemcpyDeviceToHost, D.stream));
     CU(cudaStreamSynchronize(D.stream));
     *mismatches = (long long)h;
-    CU(cudaSetDevice(cur));
     return ODAM_SQ_OK;
 }
 

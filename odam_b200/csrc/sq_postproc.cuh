@@ -1,0 +1,389 @@
+// sq_postproc.cuh -- the two geometry steps either side of the optimiser in the reference's call chain, on the device:
+//
+//   obb_of_points     compute_oriented_bbox  (reference src/utils/box_utils.py:319-410), called right after the
+//                     optimiser on the 1000 final surface points of every object (src/scripts/run_multi_view.py:66-67)
+//   box3d_iou_pair    box3d_iou              (box_utils.py:97-120 with polygon_clip :23-67, poly_area :70-73,
+//                     box3d_vol :89-95), the pair cost of merge_process (src/scripts/run_merge.py:79-122)
+//
+// compute_oriented_bbox is: xy convex hull (scipy/Qhull) -> subtract the float32 mean of the hull vertices -> for the
+// direction of every hull edge EXCEPT the closing one (last vertex -> first vertex of Qhull's vertex list) the
+// axis-aligned extent of the rotated hull -> smallest area wins (ties: smallest folded angle) -> 4 corners at z_max,
+// then the same 4 at z_min.  Which edge is "the closing one" is decided by where Qhull's vertex list starts; that is
+// reproduced here (qhull_head_facet below) instead of being defined away, because in ~1 % of the objects the skipped
+// edge is the best one and the reference then returns the runner-up rectangle.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace odam {
+
+constexpr int kHullMax = 1024;
+
+struct HullScratch {
+    uint16_t hv[kHullMax];      // hull vertices (sample indices), counter-clockwise
+    float cx[kHullMax], cy[kHullMax];   // centred hull coordinates (float32, as the reference's in-place subtraction)
+    double rarea[32];
+    double rang[32];
+    int ridx[32];
+    float wx[32], wy[32];
+    int widx[32];
+    int h, cur, start_pos, flag;
+    float curx, cury;
+    float zmin, zmax, meanx, meany;
+    double best_ang;
+};
+
+__device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) { return ax * by - ay * bx; }
+
+// gift-wrapping comparator: is candidate b a better "next counter-clockwise hull vertex after cur" than a?
+// (b strictly clockwise of a as seen from cur; collinear -> the farther one; equal points -> the lower sample index)
+__device__ __forceinline__ bool wrap_better(float cx, float cy, float ax, float ay, int ai, float bx, float by, int bi)
+{
+    if (bi < 0) return false;
+    if (ai < 0) return true;
+    const double dax = (double)ax - cx, day = (double)ay - cy, dbx = (double)bx - cx, dby = (double)by - cy;
+    const double da = dax * dax + day * day, db = dbx * dbx + dby * dby;
+    if (db == 0.0) return false;            // b coincides with cur
+    if (da == 0.0) return true;
+    const double cr = cross2(dax, day, dbx, dby);
+    if (cr != 0.0) return cr < 0.0;
+    if (db != da) return db > da;
+    return bi < ai;
+}
+
+// Where does scipy's ConvexHull(points).vertices start?  scipy walks Qhull's facet list from its head (the oldest
+// surviving facet) counter-clockwise, so vertices[0] is the first vertex of that facet.  For points in convex position
+// Qhull's build is a breadth-first quickhull: initial simplex = (min-x point, max-x point, and whichever of the min-y /
+// max-y points is farther from their line), facets in the order [(maxx,minx), (third,minx), (third,maxx)]; a facet with
+// outside points is replaced by two new facets appended to the list -- first the one that keeps the facet's OLDER
+// vertex, then the one with the younger -- split at its furthest point.  The first facet in that order with no
+// outside points is the head.  (Interior points never change this: they are never furthest.)  Verified against scipy
+// on 10^4 hulls of superquadric samples (tests/test_postproc.py).  Returns the position (in the counter-clockwise
+// list hv) of the head facet's first vertex; *flag is set when the initial simplex is so thin that Qhull may have
+// searched beyond the extreme points (not observed on superquadrics).
+__device__ int qhull_head_facet(const HullScratch &H, const float *px, const float *py, int *flag)
+{
+    const int h = H.h;
+    if (h < 3) return 0;
+    // extreme points in Qhull's point order (= sample index order): strict comparisons keep the first occurrence
+    int imin_x = 0, imax_x = 0, imin_y = 0, imax_y = 0;
+    {
+        // "first occurrence" is by sample index, not by position in the hull list
+        auto less_idx = [&](int a, int b) { return H.hv[a] < H.hv[b]; };
+        for (int k = 1; k < h; k++) {
+            const float x = px[H.hv[k]], y = py[H.hv[k]];
+            const float xn = px[H.hv[imin_x]], xx = px[H.hv[imax_x]], yn = py[H.hv[imin_y]], yx = py[H.hv[imax_y]];
+            if (x < xn || (x == xn && less_idx(k, imin_x))) imin_x = k;
+            if (x > xx || (x == xx && less_idx(k, imax_x))) imax_x = k;
+            if (y < yn || (y == yn && less_idx(k, imin_y))) imin_y = k;
+            if (y > yx || (y == yx && less_idx(k, imax_y))) imax_y = k;
+        }
+    }
+    auto X = [&](int k) { return (double)px[H.hv[k]]; };
+    auto Y = [&](int k) { return (double)py[H.hv[k]]; };
+    auto dist = [&](int u, int v, int p) { return fabs(cross2(X(v) - X(u), Y(v) - Y(u), X(p) - X(u), Y(p) - Y(u))); };
+    const int a = imin_x, b = imax_x;
+    int third = -1;
+    double bd = -1.0;
+    const int cand[2] = {imin_y, imax_y};
+    for (int c = 0; c < 2; c++) {
+        if (cand[c] == a || cand[c] == b) continue;
+        const double d = dist(a, b, cand[c]);
+        if (d > bd) { bd = d; third = cand[c]; }
+    }
+    const double len2 = (X(b) - X(a)) * (X(b) - X(a)) + (Y(b) - Y(a)) * (Y(b) - Y(a));
+    if (third < 0 || bd < 1e-2 * len2) {   // degenerate / very thin: Qhull would look at all points
+        *flag = 1;
+        third = -1; bd = -1.0;
+        for (int k = 0; k < h; k++) {
+            if (k == a || k == b) continue;
+            const double d = dist(a, b, k);
+            if (d > bd) { bd = d; third = k; }
+        }
+        if (third < 0) return 0;
+    }
+    // vertex ages (insertion order) by hull position; facets as counter-clockwise arcs u -> v of the current polygon
+    // (the outside points of facet (u, v) are the hull positions strictly between u and v)
+    constexpr int kQ = 96;   // the head is found within the first levels; a full queue falls back to position 0
+    uint16_t qu[kQ], qv[kQ], age_u[kQ], age_v[kQ];
+    int qn = 0;
+    auto push = [&](int u, int v, int au, int av) {
+        if (qn < kQ) { qu[qn] = (uint16_t)u; qv[qn] = (uint16_t)v; age_u[qn] = (uint16_t)au; age_v[qn] = (uint16_t)av; qn++; }
+    };
+    auto ccw_after = [&](int u, int v, int w) {   // is v before w when walking counter-clockwise from u?
+        const int dv = (v - u + h) % h, dw = (w - u + h) % h;
+        return dv < dw;
+    };
+    // orient each initial facet so that it is an arc of the triangle's counter-clockwise boundary
+    auto push_edge = [&](int p, int q, int ap, int aq, int other) {
+        // the arc p -> q (counter-clockwise) must not contain `other`
+        if (ccw_after(p, q, other)) push(p, q, ap, aq); else push(q, p, aq, ap);
+    };
+    push_edge(b, a, 1, 0, third);       // facet 0 omits `third`
+    push_edge(third, a, 2, 0, b);       // facet 1 omits max-x
+    push_edge(third, b, 2, 1, a);       // facet 2 omits min-x
+    int next_age = 3;
+    for (int qi = 0; qi < qn; qi++) {
+        const int u = qu[qi], v = qv[qi];
+        const int len = (v - u + h) % h;
+        if (len == 1) return u;          // no outside points: this is the head of Qhull's facet list
+        int p = -1;
+        double best = -1.0;
+        for (int s = 1; s < len; s++) {
+            const int k = (u + s) % h;
+            const double d = dist(u, v, k);
+            if (d > best) { best = d; p = k; }
+        }
+        const int ap = next_age++;
+        // two new facets: first the one that keeps the facet's older vertex, then the one with the younger
+        if (age_u[qi] < age_v[qi]) { push(u, p, age_u[qi], ap); push(p, v, ap, age_v[qi]); }
+        else { push(p, v, ap, age_v[qi]); push(u, p, age_u[qi], ap); }
+    }
+    *flag = 1;
+    return 0;
+}
+
+// Python's float modulo for a positive divisor
+__device__ __forceinline__ double py_mod_pos(double a, double b)
+{
+    double r = fmod(a, b);
+    if (r != 0.0 && r < 0.0) r += b;
+    return r;
+}
+
+// compute_oriented_bbox for the n_pts points in px/py/pz (shared memory, float32).  Whole CTA; out = 8 corners x 3.
+__device__ void obb_of_points(HullScratch &H, const float *px, const float *py, const float *pz, int n_pts,
+                              double *out /*[24]*/, int *out_flag)
+{
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    // ---- z range and the gift-wrapping start (min x, then min y, then lowest index: certainly a hull vertex) ----
+    float zmin = INFINITY, zmax = -INFINITY, sx = INFINITY, sy = INFINITY;
+    int si = -1;
+    for (int i = tid; i < n_pts; i += T) {
+        const float x = px[i], y = py[i], z = pz[i];
+        zmin = fminf(zmin, z); zmax = fmaxf(zmax, z);
+        if (si < 0 || x < sx || (x == sx && (y < sy || (y == sy && i < si)))) { sx = x; sy = y; si = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+        zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+        const float ox = __shfl_xor_sync(0xffffffffu, sx, o), oy = __shfl_xor_sync(0xffffffffu, sy, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, si, o);
+        if (oi >= 0 && (si < 0 || ox < sx || (ox == sx && (oy < sy || (oy == sy && oi < si))))) { sx = ox; sy = oy; si = oi; }
+    }
+    if (lane == 0) { H.wx[warp] = sx; H.wy[warp] = sy; H.widx[warp] = si; H.rarea[warp] = zmin; H.rang[warp] = zmax; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; w++) {
+            const float ox = H.wx[w], oy = H.wy[w];
+            const int oi = H.widx[w];
+            if (oi >= 0 && (si < 0 || ox < sx || (ox == sx && (oy < sy || (oy == sy && oi < si))))) { sx = ox; sy = oy; si = oi; }
+            zmin = fminf(zmin, (float)H.rarea[w]); zmax = fmaxf(zmax, (float)H.rang[w]);
+        }
+        H.zmin = zmin; H.zmax = zmax;
+        H.h = 1; H.flag = 0;
+        H.cur = si; H.curx = sx; H.cury = sy;
+        H.hv[0] = (uint16_t)si;
+    }
+    __syncthreads();
+    const float startx = H.curx, starty = H.cury;
+    // ---- gift wrapping, one hull vertex per round: every thread its best candidate, warp shuffle, 8 warps ----
+    const int max_rounds = min(n_pts, kHullMax - 1);
+    for (int round = 0; round <= max_rounds; round++) {
+        const float cx = H.curx, cy = H.cury;
+        float bx = 0.f, by = 0.f;
+        int bi = -1;
+        for (int i = tid; i < n_pts; i += T) {
+            const float x = px[i], y = py[i];
+            if (wrap_better(cx, cy, bx, by, bi, x, y, i)) { bx = x; by = y; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (wrap_better(cx, cy, bx, by, bi, ox, oy, oi)) { bx = ox; by = oy; bi = oi; }
+        }
+        if (lane == 0) { H.wx[warp] = bx; H.wy[warp] = by; H.widx[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < nwarps; w++)
+                if (wrap_better(cx, cy, bx, by, bi, H.wx[w], H.wy[w], H.widx[w])) { bx = H.wx[w]; by = H.wy[w]; bi = H.widx[w]; }
+            if (bi < 0 || (bx == startx && by == starty)) {
+                H.cur = -1;                      // closed (or a single point)
+            } else if (round == max_rounds) {
+                H.cur = -1; H.flag = 2;          // did not close (cannot happen with exact orientation tests)
+            } else {
+                H.hv[H.h] = (uint16_t)bi;
+                H.h = H.h + 1;
+                H.cur = bi; H.curx = bx; H.cury = by;
+            }
+        }
+        __syncthreads();
+        if (H.cur < 0) break;
+    }
+    // the start vertex must carry the lowest index among its duplicates too (it was chosen that way above)
+    const int h = H.h;
+    // ---- Qhull's vertex order: rotate so that the list starts where scipy's hull.vertices starts ----
+    if (tid == 0) {
+        int flag = 0;
+        H.start_pos = qhull_head_facet(H, px, py, &flag);
+        H.flag |= flag | (h < 3 ? 2 : 0);
+        // mean of the hull vertices in that order: sequential float32 sum, float32 division (np.mean(axis=0) of a
+        // float32 [h, 2] array), then the in-place float32 subtraction
+        float sx32 = 0.f, sy32 = 0.f;
+        for (int k = 0; k < h; k++) {
+            const int p = H.hv[(H.start_pos + k) % h];
+            sx32 = __fadd_rn(sx32, px[p]);
+            sy32 = __fadd_rn(sy32, py[p]);
+        }
+        H.meanx = __fdiv_rn(sx32, (float)h);
+        H.meany = __fdiv_rn(sy32, (float)h);
+    }
+    __syncthreads();
+    const int s0 = H.start_pos;
+    for (int k = tid; k < h; k += T) {
+        const int p = H.hv[(s0 + k) % h];
+        H.cx[k] = __fsub_rn(px[p], H.meanx);
+        H.cy[k] = __fsub_rn(py[p], H.meany);
+    }
+    __syncthreads();
+    // ---- one candidate per hull edge k -> k+1, k = 0..h-2 (the closing edge h-1 -> 0 is not considered) ----
+    const double half_pi = 1.5707963267948966;   // math.pi / 2
+    double my_area = INFINITY, my_ang = INFINITY;
+    int my_k = -1;
+    double mnx = 0, mxx = 0, mny = 0, mxy = 0;
+    for (int k = tid; k < h - 1; k += T) {
+        const float ex = __fsub_rn(H.cx[k + 1], H.cx[k]), ey = __fsub_rn(H.cy[k + 1], H.cy[k]);
+        const double ang = fabs(py_mod_pos(atan2((double)ey, (double)ex), half_pi));
+        const double c = cos(ang), s1 = cos(ang - half_pi), s2 = cos(ang + half_pi);
+        double a0 = INFINITY, a1 = -INFINITY, b0 = INFINITY, b1 = -INFINITY;
+        for (int j = 0; j < h; j++) {
+            const double x = (double)H.cx[j], y = (double)H.cy[j];
+            const double rx = c * x + s1 * y, ry = s2 * x + c * y;
+            a0 = fmin(a0, rx); a1 = fmax(a1, rx); b0 = fmin(b0, ry); b1 = fmax(b1, ry);
+        }
+        const double area = (a1 - a0) * (b1 - b0);
+        // np.unique sorts the angles ascending; the first strictly smaller area wins -> ties go to the smaller angle
+        if (area < my_area || (area == my_area && ang < my_ang)) {
+            my_area = area; my_ang = ang; my_k = k; mnx = a0; mxx = a1; mny = b0; mxy = b1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oa = __shfl_xor_sync(0xffffffffu, my_area, o), og = __shfl_xor_sync(0xffffffffu, my_ang, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, my_k, o);
+        const double t0 = __shfl_xor_sync(0xffffffffu, mnx, o), t1 = __shfl_xor_sync(0xffffffffu, mxx, o);
+        const double t2 = __shfl_xor_sync(0xffffffffu, mny, o), t3 = __shfl_xor_sync(0xffffffffu, mxy, o);
+        if (ok >= 0 && (my_k < 0 || oa < my_area || (oa == my_area && og < my_ang))) {
+            my_area = oa; my_ang = og; my_k = ok; mnx = t0; mxx = t1; mny = t2; mxy = t3;
+        }
+    }
+    if (lane == 0) { H.rarea[warp] = my_area; H.rang[warp] = my_ang; H.ridx[warp] = my_k; }
+    __syncthreads();
+    // the winning warp's lane 0 writes the result
+    bool mine = lane == 0 && my_k >= 0;
+    if (mine)
+        for (int w = 0; w < nwarps; w++) {
+            if (w == warp || H.ridx[w] < 0) continue;
+            const double oa = H.rarea[w], og = H.rang[w];
+            if (oa < my_area || (oa == my_area && (og < my_ang || (og == my_ang && w < warp)))) mine = false;
+        }
+    if (h < 3 && tid == 0) {   // degenerate input: the reference would raise inside Qhull; return the axis-aligned box
+        mine = true; my_ang = 0.0; my_area = 0.0;
+        mnx = mxx = mny = mxy = 0.0;
+    }
+    if (mine) {
+        if (!(my_area < 1e10)) { my_ang = 0.0; mnx = mxx = mny = mxy = 0.0; }   // the reference's initial min_bbox survives
+        const double c = cos(my_ang), s1 = cos(my_ang - half_pi), s2 = cos(my_ang + half_pi);
+        const double cxs[4] = {mxx, mxx, mnx, mnx}, cys[4] = {mxy, mny, mny, mxy};
+        for (int q = 0; q < 4; q++) {
+            // np.dot([x, y], R) with R = [[c, s1], [s2, c]]
+            const double X = cxs[q] * c + cys[q] * s2 + (double)H.meanx;
+            const double Y = cxs[q] * s1 + cys[q] * c + (double)H.meany;
+            out[q * 3 + 0] = X; out[q * 3 + 1] = Y; out[q * 3 + 2] = (double)H.zmax;
+            out[(q + 4) * 3 + 0] = X; out[(q + 4) * 3 + 1] = Y; out[(q + 4) * 3 + 2] = (double)H.zmin;
+        }
+        if (out_flag) *out_flag = H.flag;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// box3d_iou (box_utils.py:97-120): corners [8][3] double, upper four first; returns (iou3d, iou2d)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double poly_area2(const double *x, const double *y, int n)
+{
+    // 0.5 * |dot(x, roll(y, 1)) - dot(y, roll(x, 1))|
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < n; i++) {
+        const int j = (i + n - 1) % n;
+        a += x[i] * y[j];
+        b += y[i] * x[j];
+    }
+    return 0.5 * fabs(a - b);
+}
+
+// Sutherland-Hodgman, subject and clip given counter-clockwise (box_utils.py:23-67, same predicates and the same
+// intersection formula); returns the vertex count (0 = empty)
+__device__ int polygon_clip4(const double *sx, const double *sy, const double *cxp, const double *cyp, double *ox, double *oy)
+{
+    double ax[12], ay[12], bx[12], by[12];
+    int na = 4;
+    for (int i = 0; i < 4; i++) { ax[i] = sx[i]; ay[i] = sy[i]; }
+    double c1x = cxp[3], c1y = cyp[3];
+    for (int ci = 0; ci < 4; ci++) {
+        const double c2x = cxp[ci], c2y = cyp[ci];
+        int nb = 0;
+        double px_ = ax[na - 1], py_ = ay[na - 1];
+        auto inside = [&](double x, double y) { return (c2x - c1x) * (y - c1y) > (c2y - c1y) * (x - c1x); };
+        auto inter = [&](double s0, double s1, double e0, double e1, double &ix, double &iy) {
+            const double dcx = c1x - c2x, dcy = c1y - c2y, dpx = s0 - e0, dpy = s1 - e1;
+            const double n1 = c1x * c2y - c1y * c2x, n2 = s0 * e1 - s1 * e0;
+            const double n3 = 1.0 / (dcx * dpy - dcy * dpx);
+            ix = (n1 * dpx - n2 * dcx) * n3;
+            iy = (n1 * dpy - n2 * dcy) * n3;
+        };
+        for (int i = 0; i < na; i++) {
+            const double ex = ax[i], ey = ay[i];
+            if (inside(ex, ey)) {
+                if (!inside(px_, py_)) { inter(px_, py_, ex, ey, bx[nb], by[nb]); nb++; }
+                bx[nb] = ex; by[nb] = ey; nb++;
+            } else if (inside(px_, py_)) {
+                inter(px_, py_, ex, ey, bx[nb], by[nb]); nb++;
+            }
+            px_ = ex; py_ = ey;
+        }
+        c1x = c2x; c1y = c2y;
+        if (nb == 0) return 0;
+        na = nb;
+        for (int i = 0; i < na; i++) { ax[i] = bx[i]; ay[i] = by[i]; }
+    }
+    for (int i = 0; i < na; i++) { ox[i] = ax[i]; oy[i] = ay[i]; }
+    return na;
+}
+
+__device__ void box3d_iou_pair(const double *A, const double *B, double *iou3d, double *iou2d)
+{
+    double ax[4], ay[4], bx[4], by[4];
+    for (int i = 0; i < 4; i++) {   // corners 3, 2, 1, 0: counter-clockwise
+        ax[i] = A[(3 - i) * 3 + 0]; ay[i] = A[(3 - i) * 3 + 1];
+        bx[i] = B[(3 - i) * 3 + 0]; by[i] = B[(3 - i) * 3 + 1];
+    }
+    const double area1 = poly_area2(ax, ay, 4), area2 = poly_area2(bx, by, 4);
+    double ix[12], iy[12];
+    const int ni = polygon_clip4(ax, ay, bx, by, ix, iy);
+    // the reference takes ConvexHull(inter).volume; the clip of two convex polygons is convex, so that is its area
+    const double inter_area = ni >= 3 ? poly_area2(ix, iy, ni) : 0.0;
+    *iou2d = inter_area / (area1 + area2 - inter_area);
+    const double zmax = fmin(A[2], B[2]), zmin = fmax(A[4 * 3 + 2], B[4 * 3 + 2]);
+    const double inter_vol = inter_area * fmax(0.0, zmax - zmin);
+    auto vol = [](const double *C) {
+        auto d = [&](int i, int j) {
+            const double dx = C[i * 3] - C[j * 3], dy = C[i * 3 + 1] - C[j * 3 + 1], dz = C[i * 3 + 2] - C[j * 3 + 2];
+            return sqrt(dx * dx + dy * dy + dz * dz);
+        };
+        return d(0, 1) * d(1, 2) * d(0, 4);
+    };
+    *iou3d = inter_vol / (vol(A) + vol(B) - inter_vol);
+}
+
+}  // namespace odam

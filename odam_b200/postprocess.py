@@ -26,13 +26,15 @@ def compute_oriented_bbox(pts):
     hull-edge directions, extruded from z_min to z_max (box_utils.py:319-410, including its conventions: hull
     centred on the mean of its vertices, the closing hull edge not considered, angles folded into [0, pi/2),
     first smallest area wins, upper four corners first)."""
-    pts = np.asarray(pts, np.float64)
+    pts = np.asarray(pts)                      # the reference keeps the caller's dtype (float32 from the call site) ...
     z_min, z_max = pts[:, 2].min(), pts[:, 2].max()
     xy = pts[:, :2]
     hull = xy[ConvexHull(xy).vertices]
-    centre = hull.mean(axis=0)
+    centre = np.mean(hull, axis=0)             # ... so the mean and the centring happen in that dtype
     hull = hull - centre
-    edges = np.diff(hull, axis=0)
+    edges = np.diff(hull, axis=0).astype(np.float64)
+    hull = hull.astype(np.float64)
+    centre = centre.astype(np.float64)
     angles = np.unique(np.abs(np.arctan2(edges[:, 1], edges[:, 0]) % (np.pi / 2)))
     c, s = np.cos(angles), np.cos(angles - np.pi / 2)
     s2 = np.cos(angles + np.pi / 2)

@@ -48,3 +48,49 @@ def optimize_sharded(tracks, optimize_fn, dist, rank, world_size):
     lo, hi = parts[rank]
     local = optimize_fn(tracks.slice(lo, hi))
     return all_gather_rows(local, [h - l for l, h in parts], dist)
+
+
+def optimize_on_devices(tracks, prior, n_iters, representation, devices, **kw):
+    """ONE process driving several GPUs (the multi-device form of the call site): the packed tracks are split into
+    contiguous object blocks balanced by views, one host thread per device runs its block through the host-buffer
+    C ABI (ctypes releases the GIL; the library serialises per device, not globally), and the per-block results are
+    concatenated in object order.  Objects are batch-invariant, so the result is bit-identical to a single-device call."""
+    import threading
+    from . import api
+    parts = partition_by_views(tracks.view_off, len(devices))
+    outs, errs = [None] * len(devices), [None] * len(devices)
+
+    def work(r):
+        lo, hi = parts[r]
+        try:
+            if hi > lo:
+                outs[r] = api.optimize_host(tracks.slice(lo, hi), prior=prior, n_iters=n_iters,
+                                            representation=representation, device=devices[r], **kw)
+        except Exception as e:   # re-raised in the caller's thread
+            errs[r] = e
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    got = [o for o in outs if o is not None]
+    return {k: np.concatenate([o[k] for o in got], 0) for k in got[0]}
+
+
+def optimize_sharded_device(tracks, prior, n_iters, dist, rank, world_size, device, representation="super_quadric",
+                            out=None):
+    """One process per GPU (torchrun): every rank holds the FULL packed batch, optimises its own contiguous block on
+    `device` (one persistent launch on the current stream) and all ranks exchange the final [n, 9] parameters with one
+    NCCL all-gather issued on the same stream -- the only communication of the path.  Returns (gathered [n, 9] CUDA
+    tensor, this rank's DeviceTracks, its output dict) so that a caller can re-run the step without re-uploading."""
+    import torch
+    from . import api
+    parts = partition_by_views(tracks.view_off, world_size)
+    lo, hi = parts[rank]
+    dt = api.DeviceTracks(tracks.slice(lo, hi), device, prior)
+    res = api.optimize_device(dt, n_iters=n_iters, representation=representation, out=out)
+    full = all_gather_rows(res["params"], [h - l for l, h in parts], dist)
+    return full, dt, res

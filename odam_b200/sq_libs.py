@@ -38,28 +38,84 @@ class _Sampler:
 
 
 class SuperQuadric:
-    """Parameter container + forward sampler (reference sq_libs.py:531-595).  Picklable; leaf tensors as there."""
+    """Parameter container + forward sampler (reference sq_libs.py:531-595).  Picklable; leaf tensors as there.
+
+    The four leaf tensors (``shapes``, ``translate``, ``angle``, ``scales``: float32, requires_grad) are created the
+    first time they are read: the batched call site returns one object per track, and building four tensors for
+    each eagerly costs more than the kernel launch that optimised them all.  Until then the parameters live in one
+    packed float32[9] row (the C-ABI layout)."""
+
+    _LEAVES = {"translate": slice(0, 3), "angle": 3, "scales": slice(4, 7), "shapes": slice(7, 9)}
 
     def __init__(self, translate, angle, scales, shapes):
-        self.shapes = torch.tensor(shapes, dtype=torch.float32, requires_grad=True)
-        self.translate = torch.tensor(translate, dtype=torch.float32, requires_grad=True)
-        self.angle = torch.tensor(angle, dtype=torch.float32, requires_grad=True)
-        self.scales = torch.tensor(scales, dtype=torch.float32, requires_grad=True)  # sqrt(dim / 2)
+        p = np.empty(9, np.float32)
+        p[0:3] = np.asarray(translate, np.float64)
+        p[3] = np.float64(angle)
+        p[4:7] = np.asarray(scales, np.float64)      # sqrt(dim / 2)
+        p[7:9] = np.asarray(shapes, np.float64)
+        self.__dict__["_p"] = p
+        self.__dict__["_t"] = {}
         self.sampler = _Sampler()
+
+    @classmethod
+    def from_params(cls, p9, obj_class=None):
+        """From a packed float32[9] row [t3, yaw, s3, h2] (no tensor is built)."""
+        self = cls.__new__(cls)
+        self.__dict__["_p"] = np.array(p9, np.float32).reshape(9)
+        self.__dict__["_t"] = {}
+        self.sampler = _Sampler()
+        if obj_class is not None:
+            self.obj_class = obj_class
+        return self
+
+    # -- the reference's leaf tensors, materialised on demand ---------------------------------------------
+    def __getattr__(self, name):
+        leaves = type(self)._LEAVES
+        if name in leaves and "_t" in self.__dict__:
+            t = self.__dict__["_t"]
+            if name not in t:
+                v = self.__dict__["_p"][leaves[name]]
+                t[name] = torch.tensor(np.array(v), dtype=torch.float32, requires_grad=True)
+            return t[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in type(self)._LEAVES:
+            self.__dict__["_t"][name] = value
+        else:
+            self.__dict__[name] = value
+
+    def __getstate__(self):
+        # pickles look like the reference's: the four tensors as plain attributes
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_p", "_t")}
+        for name in type(self)._LEAVES:
+            d[name] = getattr(self, name)
+        return d
+
+    def __setstate__(self, d):
+        d = dict(d)
+        t = {name: d.pop(name) for name in type(self)._LEAVES}
+        self.__dict__.update(d)
+        self.__dict__["_t"] = t
+        self.__dict__["_p"] = np.zeros(9, np.float32)
+        self.__dict__["_p"][:] = self.params()
 
     # -- packed view ------------------------------------------------------------------------------------
     def params(self):
-        """[t3, yaw, s3, h2] float32, the C-ABI layout."""
+        """[t3, yaw, s3, h2] float32, the C-ABI layout (read from the tensors where they exist: a caller may have
+        changed them)."""
+        p = self.__dict__["_p"].copy()
         with torch.no_grad():
-            return np.concatenate([self.translate.numpy().ravel(), np.atleast_1d(self.angle.numpy()),
-                                   self.scales.numpy().ravel(), self.shapes.numpy().ravel()]).astype(np.float32)
+            for name, t in self.__dict__["_t"].items():
+                p[type(self)._LEAVES[name]] = t.detach().numpy().reshape(-1) if t.dim() else float(t)
+        return p
 
     def _set_params(self, p):
+        self.__dict__["_p"][:] = p
         with torch.no_grad():
-            self.translate.copy_(torch.from_numpy(p[0:3].copy()))
-            self.angle.copy_(torch.tensor(p[3]))
-            self.scales.copy_(torch.from_numpy(p[4:7].copy()))
-            self.shapes.copy_(torch.from_numpy(p[7:9].copy()))
+            for name, t in self.__dict__["_t"].items():   # same tensor objects, updated in place (as the reference's step)
+                v = p[type(self)._LEAVES[name]]
+                t.copy_(torch.from_numpy(np.array(v, np.float32)).reshape(t.shape))
 
     # -- reference API ----------------------------------------------------------------------------------
     def compute_ellipsoid_points(self, use_numpy):
@@ -168,10 +224,10 @@ class SuperQuadricOptimizer:
 
     def run_with_intermediate(self, gt_lines, gt_planes, Ms, n_iters=200):
         """As the reference (sq_libs.py:478-527): also the surface points and oriented box after every step."""
-        from .postprocess import compute_oriented_bbox
         hist = optimize_batch([self], [gt_lines], [Ms], n_iters, want_history=True)[0]
-        pts = api.sample_points_host(hist, device=self.device)  # [n_iters, 1000, 3] in one launch
-        steps = [{"bbox_qc": compute_oriented_bbox(pts[i]), "surface_points": pts[i]} for i in range(n_iters)]
+        # the surfaces and oriented boxes of all n_iters intermediate states from ONE launch
+        boxes, _flags, pts = api.oriented_boxes_host(hist, device=self.device, want_points=True)
+        steps = [{"bbox_qc": boxes[i], "surface_points": pts[i]} for i in range(n_iters)]
         return self.Q_init, steps
 
 

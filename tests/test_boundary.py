@@ -66,7 +66,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
     from odam_b200 import _lib
     assert set(_lib.EXPORTS) == declared
-    assert lib.odam_sq_abi_version() == 2
+    assert lib.odam_sq_abi_version() == 3
     assert lib.odam_sq_error_string(-1) == b"invalid argument"
 
 
@@ -214,3 +214,34 @@ def test_call_site_staging_matches_reference():
         assert np.allclose(get_3d_box(s["dims"], s["R"], s["t_wo"]), G[f"t{t}_bbox_dl"])
     for k in range(6):
         assert np.allclose(compute_oriented_bbox(G[f"obb{k}_pts"]), G[f"obb{k}_box"], atol=1e-9)
+
+
+def test_batched_staging_matches_reference_call_site():
+    """stage_tracks (all tracks at once) against what the reference's own optim_process derived before optimising
+    (tests/golden/optim_process.npz): the detector boxes of every track, and -- for the track with too few views, which
+    the reference returns un-optimised -- the initial quadric bit for bit."""
+    from odam_b200.run_multi_view import boxes_3d, stage_object, stage_tracks
+    G = np.load(os.path.join(REPO, "tests", "golden", "optim_process.npz"))
+    n = len(G["rows"])
+    tracks = [G[f"track{i}"] for i in range(n)]
+    st = stage_tracks(tracks, G["img_names"], int(G["img_h"]), int(G["img_w"]))
+    assert np.array_equal(st["cls"], G["obj_class"])
+    assert np.abs(boxes_3d(st["dims"], st["yaw"], st["t_wo"]) - G["bboxes_dl"]).max() < 1e-12
+    short = int(np.argmin(G["rows"]))
+    init = np.concatenate([st["t_wo"][short], [st["yaw"][short]], np.sqrt(st["dims"][short] / 2), [-0.0, -0.0]]).astype(np.float32)
+    assert np.array_equal(init, G["quadrics"][short])
+    for i in range(n):   # one by one == all at once
+        s1 = stage_object(tracks[i], G["img_names"], int(G["img_h"]), int(G["img_w"]))
+        a, b = st["view_off"][i], st["view_off"][i + 1]
+        assert np.array_equal(s1["box"], st["box"][a:b]) and np.array_equal(s1["mask"], st["mask"][a:b])
+        assert s1["valid_frames"] == st["frame_idx"][a:b].tolist() and s1["yaw"] == st["yaw"][i]
+    # shuffled rows, a duplicated frame (the first row wins, tracking_gt_utils.py:181) and unsorted frame ids
+    rng = np.random.default_rng(0)
+    t0 = tracks[0]
+    dup = np.concatenate([t0, t0[3:4] + np.array([0.0] + [1.0] * 81)[None]])
+    perm = rng.permutation(len(G["img_names"]))
+    a = stage_tracks([dup], G["img_names"][perm], int(G["img_h"]), int(G["img_w"]))
+    b = stage_tracks([t0], G["img_names"], int(G["img_h"]), int(G["img_w"]))
+    order = np.argsort(perm[a["frame_idx"]])
+    assert np.array_equal(perm[a["frame_idx"]][order], b["frame_idx"]) and np.array_equal(a["box"][order], b["box"])
+    assert stage_tracks([], G["img_names"], 968, 1296)["view_off"].tolist() == [0]

@@ -32,7 +32,7 @@ def _check(api, coracle, cfg_idx, n_objects=None, n_iters=None, sample=8, oracle
     # the launch configuration (CTA size, slices, cluster) is chosen from the batch statistics; replay the picked objects
     # with the SAME configuration so that only the batch composition differs
     cfg = api.query_launch(tracks.view_off)
-    n_param_ok = 0
+    flips = []
     for i in pick:
         # ... except the code layout on every other pick: the two builds of the kernel must agree bit for bit
         layout = cfg["code_layout"] if (i % 2 == 0 or cfg["threads"] > 256) else 3 - cfg["code_layout"]
@@ -41,15 +41,33 @@ def _check(api, coracle, cfg_idx, n_objects=None, n_iters=None, sample=8, oracle
         assert np.array_equal(one["params"][0], P[i]) and np.array_equal(one["loss"][0], L[i]), i
         a, b = tracks.view_off[i], tracks.view_off[i + 1]
         r = coracle.run(tracks.init[i], tracks.Ms[a:b], tracks.box[a:b], tracks.mask[a:b],
-                        None if prior is None else prior[tracks.cls[i]], oracle_iters)
+                        None if prior is None else prior[tracks.cls[i]], oracle_iters, record_indices=True)
         assert rel_loss(L[i, 0], r["loss"][0]) <= TOL_LOSS, i          # same state: the forward must agree
-        rp = rel_param(api.optimize_host(tracks.slice(i, i + 1), prior=prior, n_iters=oracle_iters)["params"][0],
-                       r["params"][-1]).max()
-        # a near-tie (arg-extreme point, residual sign) resolved differently by two fp32 implementations moves the
-        # parameters by up to lr; such events are rare but real -> bounded, not forbidden
-        assert rp <= 2e-2, (i, rp)
-        n_param_ok += rp <= TOL_PARAM
-    assert n_param_ok >= int(np.ceil(0.75 * len(pick))), (n_param_ok, len(pick))
+        # the kernel's discrete decisions at every one of the first iterations (the optional outputs describe the LAST
+        # iteration of a launch, so iteration k is read from a k-iteration launch of the same deterministic trajectory)
+        live = tracks.mask[a:b].astype(bool)
+        agree, worst_p, worst_l = True, 0.0, 0.0
+        for k in range(1, oracle_iters + 1):
+            o = api.optimize_host(tracks.slice(i, i + 1), prior=prior, n_iters=k,
+                                  extras=("out_arg", "out_eta_idx", "out_pred"))
+            agree &= np.array_equal(o["out_arg"].reshape(-1, 4)[live], r["arg"][k - 1][live])
+            agree &= np.array_equal(o["out_eta_idx"][0], r["eta_idx"][k - 1].astype(np.uint8))
+            agree &= np.array_equal(np.sign(o["out_pred"].reshape(-1, 4) - tracks.box[a:b])[live],
+                                    np.sign(r["pred"][k - 1] - tracks.box[a:b])[live])
+            worst_p = max(worst_p, float(rel_param(o["params"][0], r["params"][k - 1]).max()))
+            worst_l = max(worst_l, float(rel_loss(o["loss"][0], r["loss"][:k]).max()))
+        # BASELINE tolerances on every object whose decisions agree with the oracle's; a near-tie (arg-extreme point,
+        # residual sign, eta bucket) resolved differently by two fp32 implementations moves the parameters by up to
+        # lr -- such objects are counted and bounded, not exempted silently
+        if agree:
+            assert worst_p <= TOL_PARAM and worst_l <= TOL_LOSS, (i, worst_p, worst_l)
+        else:
+            flips.append((int(i), worst_p, worst_l))
+            assert worst_p <= 2e-2, (i, worst_p)
+    print(f"config {cfg_idx}: {len(pick)} sampled objects x {oracle_iters} iterations vs the C oracle: "
+          f"{len(pick) - len(flips)} agree in every discrete decision and are inside the BASELINE tolerances; "
+          f"{len(flips)} with a differently resolved near-tie: {flips}")
+    assert len(flips) <= len(pick) // 4, flips
     return L
 
 

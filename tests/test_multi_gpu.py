@@ -1,0 +1,64 @@
+"""Multi-GPU tests (need >= 2 B200s; skipped otherwise): the by-object sharding north_star names, on real devices.
+Objects are batch-invariant, so a sharded run must reproduce the single-GPU result BIT FOR BIT."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_one_process_many_devices_is_bit_identical():
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from odam_b200 import api, synthetic
+    from odam_b200.sharding import optimize_on_devices
+    tracks = api.pack_scene(synthetic.make_scene(40, 30, seed=3))
+    prior = api.prior_table()
+    one = api.optimize_host(tracks, prior=prior, n_iters=20, device=0)
+    cfg = api.query_launch(tracks.view_off)
+    two = optimize_on_devices(tracks, prior, 20, "super_quadric", [0, 1], threads=cfg["threads"],
+                              max_slices=cfg["max_slices"], cluster=cfg["cluster"], code_layout=cfg["code_layout"])
+    for k in ("params", "loss", "status"):
+        assert np.array_equal(one[k], two[k]), k
+
+
+def test_torchrun_sharded_optimise_matches_single_gpu(tmp_path):
+    """One process per GPU over NCCL, as bench.py --gpus N runs it: partition_by_views -> own block -> all-gather."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "shard.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {REPO!r})
+import numpy as np, torch, torch.distributed as dist
+from odam_b200 import api, synthetic
+from odam_b200.sharding import optimize_sharded_device
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{{rank}}"))
+tracks = api.pack_scene(synthetic.make_scene(37, 30, seed=3))
+prior = api.prior_table()
+full, dt, res = optimize_sharded_device(tracks, prior, 20, dist, rank, world, f"cuda:{{rank}}")
+torch.cuda.synchronize()
+if rank == 0:
+    one = api.optimize_device(api.DeviceTracks(tracks, "cuda:0", prior), n_iters=20,
+                              **{{k: v for k, v in api.query_launch(dt.view_off_host).items() if k in ("threads", "max_slices", "cluster", "code_layout")}})
+    torch.cuda.synchronize()
+    same = bool(torch.equal(one["params"], full))
+    print("SHARDED_EQUAL", same, tuple(full.shape))
+dist.barrier()
+dist.destroy_process_group()
+''')
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert "SHARDED_EQUAL True (37, 9)" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
