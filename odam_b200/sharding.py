@@ -59,6 +59,11 @@ def optimize_on_devices(tracks, prior, n_iters, representation, devices, **kw):
     from . import api
     parts = partition_by_views(tracks.view_off, len(devices))
     outs, errs = [None] * len(devices), [None] * len(devices)
+    # the launch configuration (CTA size, slices, cluster, code layout) is chosen from the WHOLE batch and handed to every
+    # block, so that the result does not depend on how many devices share the work (cluster sizes sum in different orders)
+    cfg = api.query_launch(tracks.view_off)
+    for k in ("threads", "max_slices", "cluster", "code_layout"):
+        kw.setdefault(k, cfg[k])
 
     def work(r):
         lo, hi = parts[r]

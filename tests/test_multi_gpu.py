@@ -24,9 +24,7 @@ def test_one_process_many_devices_is_bit_identical():
     tracks = api.pack_scene(synthetic.make_scene(40, 30, seed=3))
     prior = api.prior_table()
     one = api.optimize_host(tracks, prior=prior, n_iters=20, device=0)
-    cfg = api.query_launch(tracks.view_off)
-    two = optimize_on_devices(tracks, prior, 20, "super_quadric", [0, 1], threads=cfg["threads"],
-                              max_slices=cfg["max_slices"], cluster=cfg["cluster"], code_layout=cfg["code_layout"])
+    two = optimize_on_devices(tracks, prior, 20, "super_quadric", [0, 1])
     for k in ("params", "loss", "status"):
         assert np.array_equal(one[k], two[k]), k
 
@@ -62,3 +60,21 @@ dist.destroy_process_group()
                         "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
                        capture_output=True, text=True, timeout=600)
     assert "SHARDED_EQUAL True (37, 9)" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_call_site_sharded_over_devices_is_bit_identical():
+    """optim_process(devices=[0, 1]): the reference-facing call site with its eligible objects sharded by object."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from odam_b200 import synthetic
+    from odam_b200.run_multi_view import optim_process
+    scene = synthetic.make_scene(9, 14, seed=31)
+    seq = synthetic.scene_to_tracks(scene, [14, 14, 12, 14, 6, 11, 14, 13, 14], seed=5)
+    args = (seq["tracks"], seq["img_names"], list(seq["T_wcs"]), list(seq["P_cws"]), seq["img_h"], seq["img_w"], seq["K"],
+            "super_quadric", True, 12, 10)
+    one = optim_process(*args, device=0)
+    two = optim_process(*args, devices=[0, 1])
+    for a, b in zip(one["quadrics"], two["quadrics"]):
+        assert np.array_equal(a.params(), b.params())
+    for a, b in zip(one["bboxes_qc"], two["bboxes_qc"]):
+        assert np.array_equal(a, b)

@@ -9,7 +9,7 @@ import os
 import subprocess
 import sys
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(REPO, "gpurun_out"), os.path.join(REPO, "profiles")
 os.makedirs(P, exist_ok=True)
@@ -27,18 +27,19 @@ METRICS = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
            "launch__registers_per_thread", "launch__cluster_dim_x", "launch__grid_size", "launch__block_size")
 traffic = {}
-for cfg in (2, 4, 5):
+for cfg in (2, 3, 4, 5):
     rep = os.path.join(G, f"full_c{cfg}.ncu-rep")
     if not os.path.exists(rep):
         continue
+    cmdf = os.path.join(G, f"full_c{cfg}.cmd")
+    cmd = open(cmdf).read().strip() if os.path.exists(cmdf) else f"python tools/prof_run.py --config {cfg} --iters 40{' --objects 9472' if cfg == 5 else ''}"
     det = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     vals = dict(zip(rows[0], rows[2])) if len(rows) > 2 else {}
     units = dict(zip(rows[0], rows[1])) if len(rows) > 2 else {}
     with open(os.path.join(P, f"{tag}_ncu_full_config{cfg}.txt"), "w") as f:
-        f.write(f"ncu --set full --clock-control none --import-source on -k regex:sq_optimize -s 1 -c 1  "
-                f"python tools/prof_run.py --config {cfg} --iters 40{' --objects 9472' if cfg == 5 else ''}\n")
+        f.write(f"ncu --set full --clock-control none --import-source on -k regex:sq_optimize -s 1 -c 1  {cmd}\n")
         f.write(open(os.path.join(G, f"full_c{cfg}.log")).read() if os.path.exists(os.path.join(G, f"full_c{cfg}.log")) else "")
         f.write("\n-- selected lines of `ncu --page details` --\n")
         for line in det.splitlines():
@@ -54,6 +55,10 @@ for cfg in (2, 4, 5):
         src = subprocess.run([sys.executable, os.path.join(REPO, "tools", "ncu_source_summary.py"), rep, "25"],
                              capture_output=True, text=True).stdout
         f.write("\n-- hottest CUDA source lines (tools/ncu_source_summary.py) --\n" + src)
+        cyc = os.path.join(G, f"cycles_c{cfg}.log")
+        if os.path.exists(cyc):
+            f.write("\n-- per-phase SM cycles per iteration per object, thread 0's view (tools/prof_run.py --cycles; a separate, "
+                    "un-profiled run) --\n" + open(cyc).read())
     try:
         traffic[f"config{cfg}"] = float(vals["dram__bytes_read.sum"].replace(",", "")) * (1e6 if "Mbyte" in units.get("dram__bytes_read.sum", "") else 1e3 if "Kbyte" in units.get("dram__bytes_read.sum", "") else 1) \
             + float(vals["dram__bytes_write.sum"].replace(",", "")) * (1e6 if "Mbyte" in units.get("dram__bytes_write.sum", "") else 1e3 if "Kbyte" in units.get("dram__bytes_write.sum", "") else 1)
@@ -66,8 +71,8 @@ if traffic:
         old = json.load(open(tp))
     old.update(traffic)
     old["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE sq_optimize_kernel launch from `ncu --set full` "
-                    "(tools/prof_run.py, 40 iterations; config 5 with 9472 objects) -- bytes per launch of that capture; "
-                    "bench.py reports the config-2 figure as roofline.traffic")
+                    "(tools/prof_run.py; the command of each capture heads profiles/<round>_ncu_full_config<k>.txt) -- bytes "
+                    "per launch of that capture; bench.py reports the config-2 figure as roofline.traffic")
     json.dump(old, open(tp, "w"), indent=1)
 lc = os.path.join(G, "launches_bench.csv")
 if os.path.exists(lc):
@@ -94,9 +99,9 @@ if os.path.exists(lc):
             f.write(f"{name:92s} {n:8d} {ms:10.3f} {ms / tot:7.1%}\n")
     import shutil
     shutil.copy(lc, os.path.join(P, f"{tag}_launches_bench.csv"))
-for name in ("bench.json",):
+for name in ("bench.json", "bench_ref.json", "r02_parity.txt", "callsite.log"):
     src = os.path.join(G, name)
     if os.path.exists(src) and os.path.getsize(src) > 0:
-        with open(os.path.join(P, f"{tag}_{name}"), "w") as f:
+        with open(os.path.join(P, name if name.startswith(tag) else f"{tag}_{name}"), "w") as f:
             f.write(open(src).read())
 print("profiles/:", sorted(os.listdir(P)))
