@@ -206,7 +206,7 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
                 if (!ok) j = lower_bound_201(S.cdf, uu);
                 int k = g_k_omega[i];
                 float x0, y0, z0, X, Y, Z;
-                local_point(P, S.ge.slot[j], S.go.slot[k], x0, y0, z0);
+                local_point(P, lds_f4(&S.ge.slot[j]), lds_f4(&S.go.slot[k]), x0, y0, z0);
                 to_world(P, clamp_eps(x0), clamp_eps(y0), clamp_eps(z0), X, Y, Z);
                 S.px[i] = X; S.py[i] = Y; S.pz[i] = Z; S.pj[i] = (uint8_t)j;
             } else {  // padding: never valid (NaN is ignored by min/max)
@@ -296,19 +296,24 @@ __device__ __forceinline__ void load_M2(const float *Ms, int gv, int row, float 
 // axis this side lives on) equals the extremum `best`
 __device__ __forceinline__ int resolve_arg(const Smem &S, const float (&Mr)[4], const float (&Mz)[4], int c, float best)
 {
-    int found = -1;
+    // Every thread searches its own chunk, so at the same step neighbouring lanes would read addresses 16 words apart
+    // -- two shared-memory banks for the whole warp, a 16-way conflict (measured: 5 wavefronts per load).  Each lane
+    // therefore walks its chunk from a different starting offset; the lowest matching index wins, as before.
+    int found = kNPad;
     const int base = c * kChunk;
     const float mz3 = __fadd_rn(Mz[3], 1e-6f);  // as in the scan
+    const int rot = threadIdx.x & (kChunk - 1);
 #pragma unroll 4
-    for (int h = kChunk - 1; h >= 0; h--) {
-        const float X = S.px[base + h], Y = S.py[base + h], Z = S.pz[base + h];
+    for (int t = 0; t < kChunk; t++) {
+        const int h = base + ((t + rot) & (kChunk - 1));
+        const float X = S.px[h], Y = S.py[h], Z = S.pz[h];
         const float q = __fmaf_rn(X, Mr[0], __fmaf_rn(Y, Mr[1], __fmaf_rn(Z, Mr[2], Mr[3])));
         const float qz = __fmaf_rn(X, Mz[0], __fmaf_rn(Y, Mz[1], __fmaf_rn(Z, Mz[2], mz3)));
         float r = rcp_approx(qz);
         r = qz > 0.500001f ? r : __int_as_float(0x7fc00000);
-        if (__fmul_rn(q, r) == best) found = base + h;
+        if (__fmul_rn(q, r) == best) found = min(found, h);
     }
-    return found;
+    return found < kNPad ? found : -1;
 }
 
 #ifndef SQ_COMPACT_BLOCKS
