@@ -4,8 +4,10 @@
 mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -q -s ) > gpurun_out/r02_parity.txt 2>&1
 echo "pytest rc=$?" >> gpurun_out/r02_parity.txt
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
+# launch list of the bench command (headline step only: the sweep / strong-scaling / call-site legs generate their
+# scenes with thousands of torch kernels that would bury the list; they are timed by the un-profiled run below)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_bench.csv \
+    python bench.py --steps 5 --warmup 3 --no-cpu --no-sweep --no-strong --no-call-site > gpurun_out/bench_under_ncu.log 2>&1
 declare -A EXTRA=( [2]="" [3]="" [4]="--iters 40" [5]="--objects 2368" )
 for cfg in 2 3 4 5; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:sq_optimize -s 1 -c 1 -o gpurun_out/full_c$cfg \

@@ -91,9 +91,11 @@ if os.path.exists(lc):
         a[0] += 1; a[1] += v
     tot = sum(a[1] for a in agg.values()) or 1
     with open(os.path.join(P, f"{tag}_launches_bench.txt"), "w") as f:
-        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv  python bench.py --steps 2 --warmup 1 --no-cpu\n"
-                "(cold-cache, serialised launches: compare SHARES, not absolutes; includes the sweep configs 3/4/5 and the\n"
-                " FFMA roofline probe; torch's own kernels = scene generation + L2-flush memsets)\n\n")
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv  python bench.py --steps 5 --warmup 3 --no-cpu --no-sweep --no-strong --no-call-site\n"
+                "(cold-cache, serialised launches: compare SHARES, not absolutes.  sq_optimize_kernel = 3 warm-up + 5 timed\n"
+                " device-resident steps + 4 host-buffer (e2e) steps; inside the timed region of a step the only other launch is\n"
+                " torch's 256 MiB L2-flush fill, outside the event pair; everything else is scene generation before the timed\n"
+                " region and the FFMA roofline probe after it)\n\n")
         f.write(f"{'kernel':92s} {'launches':>8s} {'total ms':>10s} {'share':>7s}\n")
         for name, (n, ms) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{name:92s} {n:8d} {ms:10.3f} {ms / tot:7.1%}\n")
