@@ -1035,9 +1035,16 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     long items = std::max(threads, max_views);  // V * min(max_slices, threads / V) <= threads when V <= threads
     long red_offset = std::max<long>(items * 4 * 8, (long)kSpecBytes);  // phase-E results alias the B0 scratch
     long smem = red_offset + (threads / 32) * (kRed + 3) * 4;            // + cross-warp reduction rows
-    // latency regime (few, wide CTAs: shared memory is plentiful): stage each CTA's views by TMA, 68 bytes per view
+    // Each CTA's camera matrices, boxes and masks are staged into shared memory once, by TMA bulk copies (68 bytes
+    // per view): always in the latency regime (few, wide CTAs: shared memory is plentiful), and in the dense regime
+    // whenever the staging area does not cost a resident CTA (4 x 256 threads, 3 x 320 or 2 x 512 per SM)
     long stage_offset = (smem + 15) & ~15L;
-    int stage_views = (!dense && max_views <= 256) ? ((max_views + 3) & ~3) : 0;
+    int stage_views = max_views <= 256 ? ((max_views + 3) & ~3) : 0;
+    if (stage_views && dense) {
+        const long ctas = two_wide ? 2 : 1024 / threads;
+        const long per_cta = (long)sizeof(Smem) + stage_offset + (long)stage_views * 68 + 1024;   // + the driver's 1 KB
+        if (ctas * per_cta > 228L * 1024) stage_views = 0;
+    }
     if (stage_views) smem = stage_offset + (long)stage_views * 68;
     if (smem + (long)sizeof(Smem) > smem_optin) return ODAM_SQ_ERR_CONFIG;
     L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem; L.cluster = cluster; L.red_offset = (int)red_offset;
