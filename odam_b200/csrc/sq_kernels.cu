@@ -1077,7 +1077,10 @@ static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L
     OptKernel kern = pick_kernel(L.threads, L.compact);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(A.n * L.cluster); cfg.blockDim = dim3(L.threads); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+#ifndef SQ_EXTRA_SMEM
+#define SQ_EXTRA_SMEM 0   // diagnostics: unused dynamic shared memory per CTA, to lower the number of resident CTAs
+#endif
+    cfg.gridDim = dim3(A.n * L.cluster); cfg.blockDim = dim3(L.threads); cfg.dynamicSmemBytes = L.smem + SQ_EXTRA_SMEM; cfg.stream = st;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = L.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
