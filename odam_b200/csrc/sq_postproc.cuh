@@ -62,7 +62,7 @@ __device__ __forceinline__ bool wrap_better(float cx, float cy, float ax, float 
 // on 10^4 hulls of superquadric samples (tests/test_postproc.py).  Returns the position (in the counter-clockwise
 // list hv) of the head facet's first vertex; *flag is set when the initial simplex is so thin that Qhull may have
 // searched beyond the extreme points (not observed on superquadrics).
-__device__ int qhull_head_facet(const HullScratch &H, const float *px, const float *py, int *flag)
+__device__ int qhull_head_facet(HullScratch &H, const float *px, const float *py, int *flag)
 {
     const int h = H.h;
     if (h < 3) return 0;
@@ -105,11 +105,16 @@ __device__ int qhull_head_facet(const HullScratch &H, const float *px, const flo
     }
     // vertex ages (insertion order) by hull position; facets as counter-clockwise arcs u -> v of the current polygon
     // (the outside points of facet (u, v) are the hull positions strictly between u and v)
-    constexpr int kQ = 96;   // the head is found within the first levels; a full queue falls back to position 0
-    uint16_t qu[kQ], qv[kQ], age_u[kQ], age_v[kQ];
+    // the facet queue lives in the (not yet used) centred-coordinate arrays: 1024 entries of {u | v << 16} and
+    // {age_u | age_v << 16}.  On superquadric hulls the head is found within the first ~80 entries (queue length
+    // ~170); a full queue is flagged.
+    constexpr int kQ = kHullMax;
+    uint32_t *quv = reinterpret_cast<uint32_t *>(H.cx), *qage = reinterpret_cast<uint32_t *>(H.cy);
     int qn = 0;
+    bool dropped = false;
     auto push = [&](int u, int v, int au, int av) {
-        if (qn < kQ) { qu[qn] = (uint16_t)u; qv[qn] = (uint16_t)v; age_u[qn] = (uint16_t)au; age_v[qn] = (uint16_t)av; qn++; }
+        if (qn < kQ) { quv[qn] = (uint32_t)u | ((uint32_t)v << 16); qage[qn] = (uint32_t)au | ((uint32_t)av << 16); qn++; }
+        else dropped = true;
     };
     auto ccw_after = [&](int u, int v, int w) {   // is v before w when walking counter-clockwise from u?
         const int dv = (v - u + h) % h, dw = (w - u + h) % h;
@@ -125,9 +130,10 @@ __device__ int qhull_head_facet(const HullScratch &H, const float *px, const flo
     push_edge(third, b, 2, 1, a);       // facet 2 omits min-x
     int next_age = 3;
     for (int qi = 0; qi < qn; qi++) {
-        const int u = qu[qi], v = qv[qi];
+        const int u = (int)(quv[qi] & 0xffffu), v = (int)(quv[qi] >> 16);
+        const int age_u_q = (int)(qage[qi] & 0xffffu), age_v_q = (int)(qage[qi] >> 16);
         const int len = (v - u + h) % h;
-        if (len == 1) return u;          // no outside points: this is the head of Qhull's facet list
+        if (len == 1) { if (dropped) *flag = 1; return u; }   // no outside points: the head of Qhull's facet list
         int p = -1;
         double best = -1.0;
         for (int s = 1; s < len; s++) {
@@ -137,8 +143,8 @@ __device__ int qhull_head_facet(const HullScratch &H, const float *px, const flo
         }
         const int ap = next_age++;
         // two new facets: first the one that keeps the facet's older vertex, then the one with the younger
-        if (age_u[qi] < age_v[qi]) { push(u, p, age_u[qi], ap); push(p, v, ap, age_v[qi]); }
-        else { push(p, v, ap, age_v[qi]); push(u, p, age_u[qi], ap); }
+        if (age_u_q < age_v_q) { push(u, p, age_u_q, ap); push(p, v, ap, age_v_q); }
+        else { push(p, v, ap, age_v_q); push(u, p, age_u_q, ap); }
     }
     *flag = 1;
     return 0;
