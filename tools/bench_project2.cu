@@ -27,8 +27,22 @@ __device__ __forceinline__ void upd(float (&n)[4], const float (&u)[4], const fl
     n[0] = fmin3(n[0], u[2], u[3]); n[1] = fmax3(n[1], u[2], u[3]); n[2] = fmin3(n[2], w[2], w[3]); n[3] = fmax3(n[3], w[2], w[3]);
 }
 
+// the same with 2-input min/max (FMNMX: one issue cycle on the ALU pipe, partly overlapping the FMA pipe)
+__device__ __forceinline__ void upd_2in(float (&n)[4], const float (&u)[4], const float (&w)[4])
+{
+#pragma unroll
+    for (int h = 0; h < 4; h++) { n[0] = fminf(n[0], u[h]); n[1] = fmaxf(n[1], u[h]); n[2] = fminf(n[2], w[h]); n[3] = fmaxf(n[3], w[h]); }
+}
+// ... and with a pairwise pre-combine (min/max of two points first, then one 2-input update per pair and side)
+__device__ __forceinline__ void upd_tree(float (&n)[4], const float (&u)[4], const float (&w)[4])
+{
+    n[0] = fminf(n[0], fminf(fminf(u[0], u[1]), fminf(u[2], u[3]))); n[1] = fmaxf(n[1], fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3])));
+    n[2] = fminf(n[2], fminf(fminf(w[0], w[1]), fminf(w[2], w[3]))); n[3] = fmaxf(n[3], fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3])));
+}
+
 // VIEWS views per thread, GROUP points per straight-line block, 16-point chunks with chunk-id tracking as in the kernel
-template <int VIEWS, bool PACKED, int GROUP, int MINB>
+// MINMAX: 0 = 3-input FMNMX3, 1 = 2-input chain, 2 = 2-input tree
+template <int VIEWS, bool PACKED, int GROUP, int MINB, int MINMAX = 0>
 __global__ void __launch_bounds__(512, MINB) k(const float *Ms, float *out, int reps)
 {
     __shared__ __align__(16) float px[1024], py[1024], pz[1024];
@@ -56,7 +70,7 @@ __global__ void __launch_bounds__(512, MINB) k(const float *Ms, float *out, int 
                     for (int v = 0; v < VIEWS; v++) {
                         float u[4], w[4];
                         proj4<PACKED>(M[v], x, y, z, u, w);
-                        upd(n[v], u, w);
+                        if (MINMAX == 0) upd(n[v], u, w); else if (MINMAX == 1) upd_2in(n[v], u, w); else upd_tree(n[v], u, w);
                     }
                 }
             }
@@ -75,7 +89,7 @@ __global__ void __launch_bounds__(512, MINB) k(const float *Ms, float *out, int 
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
-template <int VIEWS, bool PACKED, int GROUP, int MINB>
+template <int VIEWS, bool PACKED, int GROUP, int MINB, int MINMAX = 0>
 static void run(const char *name, const float *dM, float *out, int threads, int blocks_per_sm)
 {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -83,12 +97,12 @@ static void run(const char *name, const float *dM, float *out, int threads, int 
     float ms = 0, best = 1e30f;
     for (int r = 0; r < 4; r++) {
         cudaEventRecord(e0);
-        k<VIEWS, PACKED, GROUP, MINB><<<blocks, threads>>>(dM, out, reps);
+        k<VIEWS, PACKED, GROUP, MINB, MINMAX><<<blocks, threads>>>(dM, out, reps);
         cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
         if (r && ms < best) best = ms;
     }
     const double pv = (double)blocks * threads * reps * 62 * 16 * VIEWS;
-    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k<VIEWS, PACKED, GROUP, MINB>);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k<VIEWS, PACKED, GROUP, MINB, MINMAX>);
     printf("%-44s T=%d x %d/SM regs=%3d  %.3f ms  %6.1f TFLOP/s(37)  %.2f cycles/point-view\n", name, threads, blocks_per_sm, fa.numRegs, best,
            pv * 37 / best / 1e9, best * 1e-3 * 1.965e9 * 148 * 4 / (pv / 32));
 }
@@ -104,6 +118,10 @@ int main()
         run<1, false, 16, 2>("1 view, scalar FFMA, 16-point blocks", dM, out, threads, bps);
         run<1, false, 4, 2>("1 view, scalar FFMA, 4-point blocks", dM, out, threads, bps);
         run<1, true, 16, 2>("1 view, FFMA2, 16-point blocks", dM, out, threads, bps);
+        run<1, true, 16, 2, 1>("1 view, FFMA2, 16-pt, 2-input min/max chain", dM, out, threads, bps);
+        run<1, true, 16, 2, 2>("1 view, FFMA2, 16-pt, 2-input min/max tree", dM, out, threads, bps);
+        run<1, false, 16, 2, 1>("1 view, scalar, 16-pt, 2-input min/max chain", dM, out, threads, bps);
+        run<1, false, 16, 2, 2>("1 view, scalar, 16-pt, 2-input min/max tree", dM, out, threads, bps);
         run<1, true, 8, 2>("1 view, FFMA2, 8-point blocks", dM, out, threads, bps);
         run<1, true, 4, 2>("1 view, FFMA2, 4-point blocks", dM, out, threads, bps);
         run<2, false, 4, 2>("2 views, scalar FFMA, 4-point blocks (64 regs)", dM, out, threads, bps);
