@@ -135,8 +135,10 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
                 asm volatile("bar.sync %0, %1;" ::"r"(pass), "r"(n) : "memory");
                 pool_ratios(g, sp, P.a[0], a2, t, n);
                 asm volatile("bar.sync %0, %1;" ::"r"(pass), "r"(n) : "memory");
-                pool_place(g, sp, t, n, bad);
-                asm volatile("bar.sync %0, %1;" ::"r"(pass), "r"(n) : "memory");
+                if (g.changed) {   // uniform: some split count differs from the cached tree -> replay the placement
+                    pool_place(g, sp, t, n, bad);
+                    asm volatile("bar.sync %0, %1;" ::"r"(pass), "r"(n) : "memory");
+                }
                 if (pass == 0) SQ_MARK(S, tid, 8);
             }
             if (warp == pass) {  // the grid's serial tail belongs to one warp: sampling.cpp:183-190 / :202-209
@@ -157,9 +159,11 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
         __syncthreads();
         pool_ratios(S.ge, spec[0], P.a[0], P.a[2], tid, nthreads);
         __syncthreads();
-        pool_place(S.ge, spec[0], tid, nthreads, bad);
-        if (bad) S.bad[0] = 1;
-        __syncthreads();
+        if (S.ge.changed) {   // uniform: some split count differs from the cached tree -> replay the placement
+            pool_place(S.ge, spec[0], tid, nthreads, bad);
+            if (bad) S.bad[0] = 1;
+            __syncthreads();
+        }
         SQ_MARK(S, tid, 8);
         bad = 0;
         if (warp == 0) {
@@ -174,8 +178,10 @@ __device__ __forceinline__ void sample_surface(Smem &S, GridSpec *spec, int tid,
             asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
             pool_ratios(S.go, spec[1], P.a[0], P.a[1], t1, n1);
             asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
-            pool_place(S.go, spec[1], t1, n1, bad);
-            asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
+            if (S.go.changed) {
+                pool_place(S.go, spec[1], t1, n1, bad);
+                asm volatile("bar.sync 1, %0;" ::"r"(n1) : "memory");
+            }
             if (warp == 1) pool_walk(S.go, spec[1], P.a[0], P.a[1], P.e[1], pi, -pi, g_logtab[1], pi_2, lane, bad);  // :202-209
             if (bad) S.bad[1] = 1;
         }
