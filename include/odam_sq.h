@@ -72,8 +72,8 @@ extern "C" {
 typedef struct odam_sq_options {
     int threads;            /* CTA size (multiple of 32, 64..1024); 0 = choose from the view counts   */
     int max_slices;         /* max point-slices per view (1..25); 0 = default                          */
-    int cluster;            /* CTAs per object (thread-block cluster, views tiled across them): 1, 2 or 4; 0 = auto
-                               (2 or 4 when there are fewer objects than SMs)                                 */
+    int cluster;            /* CTAs per object (thread-block cluster, views tiled across them): 1..4; 0 = auto
+                               (2, 3 or 4 when there are fewer objects than SMs)                              */
     int max_views;          /* device-pointer entry only: max views of any object, if the caller knows it
                                (with threads != 0 this avoids reading view_off back to the host)         */
     int code_layout;        /* 0 = auto.  1 = straight-line build of the kernel (16-point blocks, one copy of the sampler

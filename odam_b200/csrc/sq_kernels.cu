@@ -997,13 +997,16 @@ struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_off
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
                          int smem_optin, LaunchCfg &L)
 {
-    // view-tiled clusters: while every CTA can still have an SM to itself, 2 or 4 CTAs (on different SMs) share an
+    // view-tiled clusters: while every CTA can still have an SM to itself, 2, 3 or 4 CTAs (on different SMs) share an
     // object; long tracks (>= 128 views) are split in two in any case (finer load balance across SMs)
     int cluster = opt ? opt->cluster : 0;
+    // (3 CTAs: measured +3 % over 2 at 40..45 objects x 30..50 views; with 147 of 148 SMs asked for -- 49 objects --
+    // the clusters no longer all fit their GPCs at once and the launch is 19 % SLOWER, hence the margin)
     if (cluster == 0)
         cluster = (4 * n <= sm_count && mean_views >= 32) ? 4
+                  : (3 * n <= sm_count - sm_count / 12 && mean_views >= 24) ? 3
                   : (((2 * n <= sm_count && mean_views >= 16) || mean_views >= 128) ? 2 : 1);
-    if (cluster != 1 && cluster != 2 && cluster != 4) return ODAM_SQ_ERR_ARG;
+    if (cluster < 1 || cluster > kMaxCluster) return ODAM_SQ_ERR_ARG;
     // two regimes (measured, tools/regime_sweep.sh): "latency" = no more CTAs than SMs, one wide CTA per SM;
     // "dense" = CTAs share SMs, 256-thread CTAs
     const bool dense = n * cluster > sm_count;
