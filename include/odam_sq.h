@@ -179,6 +179,11 @@ int odam_sq_query_launch(const int32_t *view_off_host, int n, const odam_sq_opti
                          int *threads, int *smem_bytes, int *ctas_per_sm, int *cluster, int *code_layout,
                          int *max_slices);
 
+/* How many objects can get a view-tiled cluster of `cluster` CTAs (2..4) with every CTA alone on its SM of `device`
+ * (cudaOccupancyMaxActiveClusters; a cluster must fit one GPC, so this is less than SMs / cluster: 45 x 3 and 32 x 4
+ * on a 148-SM B200).  The automatic launch configuration only picks a cluster size while the objects fit. */
+int odam_sq_cluster_capacity(int device, int cluster, int *objects);
+
 #ifdef __cplusplus
 }
 #endif

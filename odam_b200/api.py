@@ -121,6 +121,18 @@ def query_launch(view_off, threads=0, max_slices=0, cluster=0, code_layout=0):
                 max_slices=ms.value)
 
 
+def cluster_capacity(device=0):
+    """{cluster size: objects that can get a cluster of that many CTAs with every CTA alone on its SM}
+    (odam_sq_cluster_capacity; 2..4)."""
+    L = _lib.load()
+    out = {}
+    for c in (2, 3, 4):
+        v = C.c_int(0)
+        _lib.check(L.odam_sq_cluster_capacity(int(device), c, C.byref(v)))
+        out[c] = v.value
+    return out
+
+
 def _options(n, SV, n_iters, threads, max_slices, m0, v0, step0, s0, extras, alloc, cluster=0, code_layout=0):
     o = _lib.Options()
     o.threads, o.max_slices, o.step0, o.cluster = int(threads), int(max_slices), int(step0), int(cluster)

@@ -927,6 +927,8 @@ struct DeviceState {
     std::vector<AdamTab> tabs;
     int sm_count = 0;
     int max_smem_optin = 0;
+    int excl_clusters[kMaxCluster + 1] = {0, 0, 0, 0, 0};   // [c]: clusters of c CTAs that can be resident at once with one
+                                                          // CTA per SM (cudaOccupancyMaxActiveClusters), 0 = unknown
     // workspace of the *_host entry points
     cudaStream_t stream = nullptr;
     void *dbuf = nullptr; size_t dbytes = 0;
@@ -981,6 +983,23 @@ static int ensure_init(int device)
         for (int threads : {256, 512, 1024})
             if (auto kern = pick_kernel(threads, compact))
                 CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
+    // How many view-tiled clusters can have every CTA on an SM of its own?  A cluster must fit one GPC, and the GPCs
+    // of a 148-SM B200 do not hold a whole number of 3- or 4-CTA clusters: measured, 45 x 3 and 32 x 4 CTAs run one
+    // per SM while 46 x 3 or 34 x 4 put two CTAs on some SMs and are 10..19 % slower than the next smaller cluster.
+    // Asking for (almost) all of an SM's shared memory makes the occupancy query count one CTA per SM.
+    for (int c = 2; c <= kMaxCluster; c++) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(c * D.sm_count); cfg.blockDim = dim3(512);
+        cfg.dynamicSmemBytes = D.max_smem_optin - (int)sizeof(Smem);
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int num = 0;
+        if (cudaOccupancyMaxActiveClusters(&num, sq_optimize_kernel<512, false>, &cfg) == cudaSuccess) D.excl_clusters[c] = num;
+        else cudaGetLastError();
+    }
     CU(cudaFuncSetAttribute(sq_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaFuncSetAttribute(sq_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
     CU(cudaFuncSetAttribute(sq_angles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem));
@@ -995,17 +1014,24 @@ struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_off
 
 // view statistics -> CTA size.  Small tracks get several point slices per view so that a CTA has >=4 warps.
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
-                         int smem_optin, LaunchCfg &L)
+                         int smem_optin, const int *excl_clusters, LaunchCfg &L)
 {
+    // objects that can have a cluster of c CTAs each with every CTA alone on its SM (see ensure_init); the fallback
+    // margins are the measured B200 numbers (45 clusters of 3, 32 of 4)
+    auto fits = [&](int c) {
+        const int cap = excl_clusters && excl_clusters[c] > 0 ? excl_clusters[c]
+                        : (c == 2 ? sm_count / 2 : c == 3 ? (sm_count - sm_count / 12) / 3 : (sm_count - sm_count / 8) / 4);
+        return n <= cap;
+    };
     // view-tiled clusters: while every CTA can still have an SM to itself, 2, 3 or 4 CTAs (on different SMs) share an
     // object; long tracks (>= 128 views) are split in two in any case (finer load balance across SMs)
     int cluster = opt ? opt->cluster : 0;
     // (3 CTAs: measured +3 % over 2 at 40..45 objects x 30..50 views; with 147 of 148 SMs asked for -- 49 objects --
     // the clusters no longer all fit their GPCs at once and the launch is 19 % SLOWER, hence the margin)
     if (cluster == 0)
-        cluster = (4 * n <= sm_count && mean_views >= 32) ? 4
-                  : (3 * n <= sm_count - sm_count / 12 && mean_views >= 24) ? 3
-                  : (((2 * n <= sm_count && mean_views >= 16) || mean_views >= 128) ? 2 : 1);
+        cluster = (fits(4) && mean_views >= 32) ? 4
+                  : (fits(3) && mean_views >= 24) ? 3
+                  : (((fits(2) && mean_views >= 16) || mean_views >= 128) ? 2 : 1);
     if (cluster < 1 || cluster > kMaxCluster) return ODAM_SQ_ERR_ARG;
     // two regimes (measured, tools/regime_sweep.sh): "latency" = no more CTAs than SMs, one wide CTA per SM;
     // "dense" = CTAs share SMs, 256-thread CTAs
@@ -1145,6 +1171,15 @@ const char *odam_sq_last_cuda_error(void) { return g_cuda_err; }
 
 int odam_sq_init(int device) { return ensure_init(device); }
 
+int odam_sq_cluster_capacity(int device, int cluster, int *objects)
+{
+    if (!objects || cluster < 2 || cluster > kMaxCluster) return ODAM_SQ_ERR_ARG;
+    int rc = ensure_init(device);
+    if (rc) return rc;
+    *objects = g_dev[device].excl_clusters[cluster];
+    return ODAM_SQ_OK;
+}
+
 int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *opt, int *threads, int *smem_bytes,
                          int *ctas_per_sm, int *cluster, int *code_layout, int *max_slices)
 {
@@ -1153,16 +1188,18 @@ int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *
     for (int i = 0; i < n; i++) maxv = std::max(maxv, view_off[i + 1] - view_off[i]);
     LaunchCfg L;
     int sm_count = 148, smem_optin = 232448;   // B200; the current device's own numbers once it is initialised
+    const int *excl = nullptr;
     {
         int dev = -1;
         if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_dev[dev].ready) {
             sm_count = g_dev[dev].sm_count;
             smem_optin = g_dev[dev].max_smem_optin;
+            excl = g_dev[dev].excl_clusters;
         } else {
             cudaGetLastError();
         }
     }
-    int rc = choose_launch(maxv, (double)(view_off[n] - view_off[0]) / n, n, opt, sm_count, smem_optin, L);
+    int rc = choose_launch(maxv, (double)(view_off[n] - view_off[0]) / n, n, opt, sm_count, smem_optin, excl, L);
     if (rc) return rc;
     if (threads) *threads = L.threads;
     if (cluster) *cluster = L.cluster;
@@ -1206,7 +1243,7 @@ int odam_sq_optimize(const float *init, const int32_t *cls, const int32_t *view_
         meanv = (double)(voff[n] - voff[0]) / n;
     }
     LaunchCfg L;
-    rc = choose_launch(maxv, meanv, n, opt, D.sm_count, D.max_smem_optin, L);
+    rc = choose_launch(maxv, meanv, n, opt, D.sm_count, D.max_smem_optin, D.excl_clusters, L);
     if (rc) return rc;
     // Adam bias-correction table (host doubles, as torch computes them in Python floats); one cached table per
     // (stream, schedule), so launches on different streams never share -- or overwrite -- each other's table
@@ -1313,7 +1350,7 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
     CU(guard.enter(device));
     std::lock_guard<std::mutex> host_lock(D.host_mu);
     LaunchCfg L;
-    rc = choose_launch(maxv, (double)SV / n, n, opt, D.sm_count, D.max_smem_optin, L);
+    rc = choose_launch(maxv, (double)SV / n, n, opt, D.sm_count, D.max_smem_optin, D.excl_clusters, L);
     if (rc) return rc;
 
     // one packed staging buffer: inputs first, outputs after; same layout on host (pinned) and device
