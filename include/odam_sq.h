@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define ODAM_SQ_ABI_VERSION 3
+#define ODAM_SQ_ABI_VERSION 4
 #define ODAM_SQ_N_SAMPLES 1000 /* sq_libs.py:545  EqualDistanceSamplerSQ(1000) */
 #define ODAM_SQ_GRID 201       /* _sampler.pyx:423 buffer_size */
 #define ODAM_SQ_N_PARAMS 9
@@ -96,6 +96,11 @@ typedef struct odam_sq_options {
     float *out_param_hist;  /* [n][n_iters][9] parameters after every step                             */
     int64_t *out_cycles;    /* device-pointer entry only: [n][16] SM cycles per phase as seen by thread 0, summed over iterations
                                (see tools/prof_run.py for the slot names) */
+    /* the step that follows the optimiser at the reference's call site (run_multi_view.py:66-67), fused behind it:
+       a second launch on the same stream samples the final surfaces and computes their oriented boxes (see
+       odam_sq_oriented_boxes) -- one call, one synchronisation, one copy back instead of two                    */
+    double *out_corners;    /* [n][8][3] oriented boxes of the optimised objects (NULL = not wanted)             */
+    int32_t *out_box_flag;  /* [n] flags of odam_sq_oriented_boxes (may be NULL)                                 */
 } odam_sq_options;
 
 int odam_sq_abi_version(void);

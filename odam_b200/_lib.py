@@ -28,7 +28,8 @@ class Options(C.Structure):
                 ("m0", C.c_void_p), ("v0", C.c_void_p), ("step0", C.c_int), ("s0", C.c_void_p),
                 ("out_m", C.c_void_p), ("out_v", C.c_void_p), ("out_grad", C.c_void_p), ("out_pred", C.c_void_p),
                 ("out_arg", C.c_void_p), ("out_eta_idx", C.c_void_p), ("out_grids", C.c_void_p),
-                ("out_param_hist", C.c_void_p), ("out_cycles", C.c_void_p)]
+                ("out_param_hist", C.c_void_p), ("out_cycles", C.c_void_p),
+                ("out_corners", C.c_void_p), ("out_box_flag", C.c_void_p)]
 
 
 class OdamSqError(RuntimeError):

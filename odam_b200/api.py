@@ -144,7 +144,8 @@ def _options(n, SV, n_iters, threads, max_slices, m0, v0, step0, s0, extras, all
     shapes = dict(out_m=((n, 9), np.float32), out_v=((n, 9), np.float32), out_grad=((n, 9), np.float32),
                   out_pred=((SV, 4), np.float32), out_arg=((SV, 4), np.int32),
                   out_eta_idx=((n, _lib.N_SAMPLES), np.uint8), out_grids=((n, 2, _lib.GRID), np.float32),
-                  out_param_hist=((n, n_iters, 9), np.float32))
+                  out_param_hist=((n, n_iters, 9), np.float32),
+                  out_corners=((n, 8, 3), np.float64), out_box_flag=(n, np.int32))
     for name in extras:
         keep[name] = alloc(None, *shapes[name])
     return o, keep
@@ -157,7 +158,8 @@ def optimize_host(tracks, prior=None, n_iters=200, representation="super_quadric
 
     prior: None (no prior term) or an [8,9] float32 table (see prior_table()).
     extras: names of optional outputs of odam_sq_options (out_m, out_v, out_grad, out_pred, out_arg,
-            out_eta_idx, out_grids, out_param_hist).
+            out_eta_idx, out_grids, out_param_hist; out_corners (+ out_box_flag): the oriented boxes of the optimised
+            objects, computed by a second launch fused behind the optimiser inside the same call).
     """
     L = _lib.load()
     n, SV = tracks.n, tracks.total_views
@@ -281,8 +283,10 @@ class DeviceTracks:
 
 
 def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr_shape=0.1, threads=0,
-                    max_slices=0, out=None, cycles=None, cluster=0, code_layout=0):
-    """Enqueue one fused launch on torch's current stream; returns dict of CUDA tensors (no sync)."""
+                    max_slices=0, out=None, cycles=None, cluster=0, code_layout=0, corners=None):
+    """Enqueue one fused launch on torch's current stream; returns dict of CUDA tensors (no sync).
+    corners: optional float64 CUDA tensor [n, 8, 3] -- the oriented boxes of the optimised objects, from a second launch
+    enqueued right behind the optimiser (odam_sq_options.out_corners)."""
     torch = dt.torch
     L = _lib.load()
     if out is None:
@@ -301,6 +305,12 @@ def optimize_device(dt, n_iters=200, representation="super_quadric", lr=0.01, lr
                 or cycles.device != dt.device:
             raise ValueError("cycles must be a contiguous int64 CUDA tensor of shape [n, 16] on the tracks' device")
         o.out_cycles = cycles.data_ptr()
+    if corners is not None:
+        if tuple(corners.shape) != (dt.n, 8, 3) or corners.dtype != torch.float64 or not corners.is_contiguous() \
+                or corners.device != dt.device:
+            raise ValueError("corners must be a contiguous float64 CUDA tensor of shape [n, 8, 3] on the tracks' device")
+        o.out_corners = corners.data_ptr()
+        out["corners"] = corners
     p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
     with torch.cuda.device(dt.device):
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)

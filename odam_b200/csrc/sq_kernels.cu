@@ -1291,7 +1291,13 @@ int odam_sq_optimize(const float *init, const int32_t *cls, const int32_t *view_
         A.out_param_hist = opt->out_param_hist;
         A.out_cycles = (long long *)opt->out_cycles;
     }
-    return launch_optimize(D, A, L, st);
+    rc = launch_optimize(D, A, L, st);
+    if (rc) return rc;
+    if (opt && opt->out_corners) {   // run_multi_view.py:66-67 right behind the optimiser, same stream
+        sq_obb_kernel<<<n, 256, kFwdSmem, st>>>(out_params, n, opt->out_corners, opt->out_box_flag, nullptr);
+        CU(cudaGetLastError());
+    }
+    return ODAM_SQ_OK;
 }
 
 int odam_sq_sample_points(const float *params, int n, float *out_xyz, void *stream)
@@ -1356,7 +1362,7 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
     // one packed staging buffer: inputs first, outputs after; same layout on host (pinned) and device
     size_t in_bytes = 0, total = 0;
     size_t o_init, o_cls, o_voff, o_Ms, o_box, o_mask, o_prior, o_tab, o_m0, o_v0, o_s0;
-    size_t o_par, o_loss, o_st, o_m, o_v, o_g, o_pred, o_arg, o_eta, o_grids, o_hist;
+    size_t o_par, o_loss, o_st, o_m, o_v, o_g, o_pred, o_arg, o_eta, o_grids, o_hist, o_cor, o_flag;
     auto lay = [&](Carver &C) {
         o_init = C.take<float>((size_t)n * 9); o_cls = C.take<int32_t>(n);
         o_voff = C.take<int32_t>(n + 1); o_Ms = C.take<float>(SV * 12);
@@ -1373,6 +1379,8 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
         o_eta = C.take<uint8_t>(opt && opt->out_eta_idx ? (size_t)n * kN : 0);
         o_grids = C.take<float>(opt && opt->out_grids ? (size_t)n * 2 * kG : 0);
         o_hist = C.take<float>(opt && opt->out_param_hist ? (size_t)n * n_iters * 9 : 0);
+        o_cor = C.take<double>(opt && opt->out_corners ? (size_t)n * 24 : 0);
+        o_flag = C.take<int32_t>(opt && opt->out_corners ? n : 0);
         total = C.off;
     };
     { Carver C; lay(C); }
@@ -1419,6 +1427,10 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
     }
     rc = launch_optimize(D, A, L, st);
     if (rc) return rc;
+    if (opt && opt->out_corners) {   // run_multi_view.py:66-67 right behind the optimiser: no second call, copy or sync
+        sq_obb_kernel<<<n, 256, kFwdSmem, st>>>((float *)(d + o_par), n, (double *)(d + o_cor), (int32_t *)(d + o_flag), nullptr);
+        CU(cudaGetLastError());
+    }
     CU(cudaMemcpyAsync(h + in_bytes, d + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(out_params, h + o_par, sizeof(float) * 9 * n);
@@ -1433,6 +1445,8 @@ int odam_sq_optimize_host(const float *init, const int32_t *cls, const int32_t *
         if (opt->out_eta_idx) memcpy(opt->out_eta_idx, h + o_eta, (size_t)n * kN);
         if (opt->out_grids) memcpy(opt->out_grids, h + o_grids, sizeof(float) * 2 * kG * n);
         if (opt->out_param_hist) memcpy(opt->out_param_hist, h + o_hist, sizeof(float) * 9 * (size_t)n * n_iters);
+        if (opt->out_corners) memcpy(opt->out_corners, h + o_cor, sizeof(double) * 24 * n);
+        if (opt->out_corners && opt->out_box_flag) memcpy(opt->out_box_flag, h + o_flag, sizeof(int32_t) * n);
     }
     return ODAM_SQ_OK;
 }

@@ -9,8 +9,9 @@ Qhull call per object); here
      of the per-frame yaws (closed form for rotations about z instead of scipy's ``Rotation.mean`` per object), mean dims,
      and for every usable frame the detected box sides with the 20 px border rule -- straight into the packed C-ABI arrays;
   2. every eligible object is optimised by ONE persistent kernel launch (``odam_sq_optimize_host``);
-  3. ONE more launch samples all final surfaces and computes their oriented boxes on the device
-     (``odam_sq_oriented_boxes_host``: convex hull + min-area rectangle, csrc/sq_postproc.cuh).
+  3. ONE more launch, enqueued behind it inside the same call (``odam_sq_options.out_corners``), samples all final
+     surfaces and computes their oriented boxes on the device (convex hull + min-area rectangle,
+     csrc/sq_postproc.cuh) -- one synchronisation and one copy back for both.
 
 Staging restates only what the optimiser consumes of ``tracking_gt_utils.load_pred_object`` (:145-211) and skips what
 it never reads (plane vectors, depth planes).  Track rows are the 82-float layout of processor.py:98-108.
@@ -168,13 +169,16 @@ def optim_process(tracks, img_names, T_wcs, P_cws, img_h, img_w, K, representati
             from .sharding import optimize_on_devices
             out = optimize_on_devices(packed, table, n_iters, representation, devices)
         else:
-            out = api.optimize_host(packed, prior=table, n_iters=n_iters, representation=representation, device=device)
+            out = api.optimize_host(packed, prior=table, n_iters=n_iters, representation=representation, device=device,
+                                    extras=("out_corners", "out_box_flag"))   # :66-67 fused behind the optimiser
         bad = np.nonzero(out["status"] & _lib.ST_NONFINITE)[0]
         if bad.size:
             raise RuntimeError(f"superquadric optimisation produced NaN/Inf for object(s) {run[bad].tolist()} "
                                "(the reference raises from torch anomaly mode, sq_libs.py:456)")
         params[run] = out["params"]
-        corners, _flags = api.oriented_boxes_host(out["params"], device=device)   # :66-67, one launch
+        corners = out.get("out_corners")
+        if corners is None:   # sharded over several devices: one more launch for all surfaces + oriented boxes
+            corners, _flags = api.oriented_boxes_host(out["params"], device=device)   # :66-67
         bboxes_qc[run] = corners
     quadrics = [SuperQuadric.from_params(params[i], int(st["cls"][i])) for i in range(n)]
     return {"tracks": tracks, "bboxes_qc": list(bboxes_qc), "bboxes_dl": list(bboxes_dl), "quadrics": quadrics}

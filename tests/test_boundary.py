@@ -66,7 +66,7 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
     from odam_b200 import _lib
     assert set(_lib.EXPORTS) == declared
-    assert lib.odam_sq_abi_version() == 3
+    assert lib.odam_sq_abi_version() == 4
     assert lib.odam_sq_error_string(-1) == b"invalid argument"
 
 

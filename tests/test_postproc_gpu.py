@@ -51,6 +51,31 @@ def test_oriented_boxes_from_params_vs_host_mirror(api):
     assert len(bad) <= 1
 
 
+def test_oriented_boxes_fused_behind_the_optimiser(api):
+    """odam_sq_options.out_corners: the oriented boxes come out of the optimiser call itself (second launch on the same
+    stream, one copy back) and are bit-identical to the stand-alone entry run on the returned parameters -- through the
+    host-buffer entry and through the device-pointer entry."""
+    import torch
+
+    from odam_b200 import synthetic
+    scene = synthetic.make_scene(7, 20, seed=21)
+    tracks = api.pack_scene(scene)
+    prior = api.prior_table()
+    out = api.optimize_host(tracks, prior=prior, n_iters=6, extras=("out_corners", "out_box_flag"))
+    plain = api.optimize_host(tracks, prior=prior, n_iters=6)
+    assert np.array_equal(out["params"], plain["params"]) and np.array_equal(out["loss"], plain["loss"])
+    want, flags = api.oriented_boxes_host(out["params"])
+    assert np.array_equal(out["out_corners"], want) and np.array_equal(out["out_box_flag"], flags)
+    assert np.isfinite(want).all() and np.abs(want).max() > 0
+    # device-pointer entry
+    dt = api.DeviceTracks(tracks, "cuda:0", prior)
+    corners = torch.zeros((tracks.n, 8, 3), dtype=torch.float64, device="cuda:0")
+    dev = api.optimize_device(dt, n_iters=6, corners=corners)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["params"].cpu().numpy(), out["params"])
+    assert np.array_equal(dev["corners"].cpu().numpy(), want)
+
+
 def test_merge_cost_matrix_matches_reference_box3d_iou(api):
     """1 - box3d_iou for every pair i < j of 32 boxes (axis-aligned-extruded oriented boxes incl. near-duplicates, a
     far-away box and six optimiser outputs) against the reference's own box3d_iou; then the class gating of
