@@ -542,8 +542,8 @@ def time_call_site(scene, cfg, device):
     units = float(scene.n * scene.V * cfg["n_iters"])
     return {"value": units / (ms / 1e3), "unit": UNIT, "ms_per_call": ms, "calls": 5, "objects": scene.n, "views": scene.V,
             "entry": "odam_b200.run_multi_view.optim_process(tracks, img_names, T_wcs, P_cws, h, w, K, 'super_quadric', "
-                     "prior, n_iters, n_views): vectorised staging, H2D, one optimiser launch, D2H, one oriented-box "
-                     "launch, result objects",
+                     "prior, n_iters, n_views): vectorised staging, H2D, one optimiser launch + one oriented-box launch "
+                     "behind it in the same C-ABI call, D2H, result objects",
             "returned": sorted(out)}
 
 
