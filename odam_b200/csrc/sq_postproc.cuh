@@ -42,6 +42,16 @@ __device__ __forceinline__ bool wrap_better(float cx, float cy, float ax, float 
 {
     if (bi < 0) return false;
     if (ai < 0) return true;
+    {
+        // float32 filter: the sign of the orientation determinant is certain when it exceeds the rounding error of
+        // its own evaluation (four subtractions, two products, one difference: < 4 * 2^-24 of |p1| + |p2|; the
+        // threshold leaves a factor 4).  Coincident points and collinear triples give 0 here and take the exact path.
+        const float fax = ax - cx, fay = ay - cy, fbx = bx - cx, fby = by - cy;
+        const float p1 = fax * fby, p2 = fay * fbx;
+        const float cr32 = p1 - p2;
+        const float mag = fabsf(p1) + fabsf(p2);
+        if (mag > 1e-30f && fabsf(cr32) > 1e-6f * mag) return cr32 < 0.f;   // (no verdict from denormal products)
+    }
     const double dax = (double)ax - cx, day = (double)ay - cy, dbx = (double)bx - cx, dby = (double)by - cy;
     const double da = dax * dax + day * day, db = dbx * dbx + dby * dby;
     if (db == 0.0) return false;            // b coincides with cur
@@ -211,9 +221,17 @@ __device__ void obb_of_points(HullScratch &H, const float *px, const float *py, 
         }
         if (lane == 0) { H.wx[warp] = bx; H.wy[warp] = by; H.widx[warp] = bi; }
         __syncthreads();
+        if (warp == 0) {   // the warps' candidates meet in warp 0: one per lane, the same butterfly once more
+            bi = lane < nwarps ? H.widx[lane] : -1;
+            bx = lane < nwarps ? H.wx[lane] : 0.f;
+            by = lane < nwarps ? H.wy[lane] : 0.f;
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (wrap_better(cx, cy, bx, by, bi, ox, oy, oi)) { bx = ox; by = oy; bi = oi; }
+            }
+        }
         if (tid == 0) {
-            for (int w = 1; w < nwarps; w++)
-                if (wrap_better(cx, cy, bx, by, bi, H.wx[w], H.wy[w], H.widx[w])) { bx = H.wx[w]; by = H.wy[w]; bi = H.widx[w]; }
             if (bi < 0 || (bx == startx && by == starty)) {
                 H.cur = -1;                      // closed (or a single point)
             } else if (round == max_rounds) {
