@@ -70,7 +70,8 @@ def stage_tracks(tracks, frame_ids, img_h, img_w):
         z = np.zeros
         return dict(cls=z(n, np.int32), t_wo=z((n, 3)), yaw=z(n), dims=z((n, 3)), view_off=z(n + 1, np.int32),
                     frame_idx=z(0, np.int64), box=z((0, 4), np.float32), mask=z((0, 4), np.uint8), n_present=z(n, np.int64))
-    cat = np.concatenate([np.asarray(t, np.float64).reshape(-1, 82) for t in tracks], 0)
+    # only the first 13 of the 82 columns are read here: frame, class, box (4), dims (3), centre (3), yaw
+    cat = np.concatenate([np.asarray(t, np.float64).reshape(-1, 82)[:, :13] for t in tracks], 0)
     obj = np.repeat(np.arange(n), rows_per)
     starts = np.concatenate([[0], np.cumsum(rows_per)[:-1]])
     # class: int(np.median(column)) per track
