@@ -325,7 +325,11 @@ __device__ __forceinline__ int resolve_arg(const Smem &S, const float (&Mr)[4], 
 #ifndef SQ_COMPACT_BLOCKS
 #define SQ_COMPACT_BLOCKS 4
 #endif
-#define SQ_MIN_BLOCKS(threads, compact) ((compact) ? SQ_COMPACT_BLOCKS : 1024 / (threads))
+// Resident CTAs per SM the register allocation aims at: the compact build 4 x 256 threads, the straight-line build 1024
+// threads' worth (64 registers each) -- except kSolo, the build for launches where every CTA has an SM to itself (the
+// latency regime): one 512-thread CTA may then use 128 registers per thread, which removes every spill and most of
+// the rematerialised address arithmetic from the serial phases (+3..6 % there, bit-identical results).
+#define SQ_MIN_BLOCKS(threads, compact, solo) ((compact) ? SQ_COMPACT_BLOCKS : ((solo) ? 1 : 1024 / (threads)))
 // phase-E work item -> view << 16 | first chunk << 8 | end chunk: item = slice * V + view, the 63 chunks split evenly
 __device__ __forceinline__ unsigned item_code(int item, int V, int slices)
 {
@@ -334,8 +338,8 @@ __device__ __forceinline__ unsigned item_code(int item, int V, int slices)
 }
 
 // kCompact selects the small-instruction-footprint build (odam_sq_options::code_layout): same arithmetic either way.
-template <int kMaxThreads, bool kCompact>
-__global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompact)) sq_optimize_kernel(OptArgs A)
+template <int kMaxThreads, bool kCompact, bool kSolo = false>
+__global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompact, kSolo)) sq_optimize_kernel(OptArgs A)
 {
     // fixed state in static shared memory (compile-time addresses), per-launch scratch in dynamic shared memory
     __shared__ Smem S;
@@ -941,8 +945,9 @@ using OptKernel = void (*)(OptArgs);
 
 // every instantiation is capped at 64 registers/thread (1024 resident threads per SM worth of registers); the compact
 // layout only exists for CTAs of up to 256 threads (it is for many small CTAs per SM)
-static OptKernel pick_kernel(int threads, int compact)
+static OptKernel pick_kernel(int threads, int compact, int solo = 0)
 {
+    if (solo && !compact && threads <= 512) return sq_optimize_kernel<512, false, true>;   // one CTA per SM: 128 registers
     if (compact) return threads <= 256 ? sq_optimize_kernel<256, true> : nullptr;
     return threads <= 256 ? sq_optimize_kernel<256, false>
                           : (threads <= 512 ? sq_optimize_kernel<512, false> : sq_optimize_kernel<1024, false>);
@@ -983,6 +988,7 @@ static int ensure_init(int device)
         for (int threads : {256, 512, 1024})
             if (auto kern = pick_kernel(threads, compact))
                 CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
+    CU(cudaFuncSetAttribute(pick_kernel(512, 0, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
     // How many view-tiled clusters can have every CTA on an SM of its own?  A cluster must fit one GPC, and the GPCs
     // of a 148-SM B200 do not hold a whole number of 3- or 4-CTA clusters: measured, 45 x 3 and 32 x 4 CTAs run one
     // per SM while 46 x 3 or 34 x 4 put two CTAs on some SMs and are 10..19 % slower than the next smaller cluster.
@@ -1010,7 +1016,7 @@ static int ensure_init(int device)
 }
 
 constexpr double kCompactMaxViews = 40;  // mean views per CTA up to which the compact layout wins (measured)
-struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_offset, stage_views, compact; };
+struct LaunchCfg { int threads, max_slices, smem, cluster, red_offset, stage_offset, stage_views, compact, solo; };
 
 // view statistics -> CTA size.  Small tracks get several point slices per view so that a CTA has >=4 warps.
 static int choose_launch(int max_views, double mean_views, int n, const odam_sq_options *opt, int sm_count,
@@ -1084,6 +1090,7 @@ static int choose_launch(int max_views, double mean_views, int n, const odam_sq_
     if (smem + (long)sizeof(Smem) > smem_optin) return ODAM_SQ_ERR_CONFIG;
     L.threads = threads; L.max_slices = max_slices; L.smem = (int)smem; L.cluster = cluster; L.red_offset = (int)red_offset;
     L.stage_offset = (int)stage_offset; L.stage_views = stage_views; L.compact = layout == 2;
+    L.solo = !dense;   // every CTA alone on its SM
     return ODAM_SQ_OK;
 }
 
@@ -1109,7 +1116,7 @@ static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L
     A.red_offset = L.red_offset;
     A.stage_offset = L.stage_offset; A.stage_views = L.stage_views;
     if (A.out_status) CU(cudaMemsetAsync(A.out_status, 0, sizeof(int32_t) * A.n, st));  // CTAs OR their flags in
-    OptKernel kern = pick_kernel(L.threads, L.compact);
+    OptKernel kern = pick_kernel(L.threads, L.compact, L.solo);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
 #ifndef SQ_EXTRA_SMEM
