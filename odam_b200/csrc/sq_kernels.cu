@@ -1214,7 +1214,8 @@ int odam_sq_query_launch(const int32_t *view_off, int n, const odam_sq_options *
     if (max_slices) *max_slices = L.max_slices;
     if (smem_bytes) *smem_bytes = L.smem;
     if (smem_bytes) *smem_bytes += (int)sizeof(Smem);
-    if (ctas_per_sm) *ctas_per_sm = std::min({32, 2048 / L.threads, 65536 / (64 * L.threads), (233472 - 1024) / (L.smem + (int)sizeof(Smem) + 1024)});
+    const int regs = (L.solo && !L.compact && L.threads <= 512) ? 128 : 64;   // the build pick_kernel() selects
+    if (ctas_per_sm) *ctas_per_sm = std::min({32, 2048 / L.threads, 65536 / (regs * L.threads), (233472 - 1024) / (L.smem + (int)sizeof(Smem) + 1024)});
     return ODAM_SQ_OK;
 }
 
