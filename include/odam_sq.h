@@ -184,6 +184,21 @@ int odam_sq_query_launch(const int32_t *view_off_host, int n, const odam_sq_opti
                          int *threads, int *smem_bytes, int *ctas_per_sm, int *cluster, int *code_layout,
                          int *max_slices);
 
+/* Host-side staging of the reference's call site (src/scripts/run_multi_view.py:31-58; load_pred_object,
+ * src/utils/tracking_gt_utils.py:145-211, averaging_T_wos :59-66, the 20 px border rule of
+ * src/super_quadric/quadric_helper.py:87-107) for all tracks of a call, in native code: no CUDA, callable without a GPU.
+ * tracks[i] points to track i's rows (double, row_stride doubles apart, the 82-column layout of processor.py:98-108;
+ * columns 0 frame id, 1 class, 2..5 box x_min y_min x_max y_max, 6..8 dims, 9..11 centre, 12 yaw are read),
+ * rows_per[i] is its row count, frame_ids[n_frames] the frames of this call.  Per track: cls = int(median(class)),
+ * t_wo[3] = mean centre over all rows, yaw = chordal mean of the yaws of the frames present (first row per frame),
+ * dims[3] = their mean, n_present = their count; and CSR-packed per usable frame (at least one box side farther than
+ * 20 px from the image border): view_off[n+1], frame_idx (index into frame_ids), box [.][4] / mask [.][4] in the
+ * order x_min, x_max, y_min, y_max (absent sides 0) -- sized by the caller for sum(rows_per) entries. */
+int odam_sq_stage_tracks_host(const double *const *tracks, const int64_t *rows_per, int n, int row_stride,
+                              const int64_t *frame_ids, int n_frames, int img_h, int img_w,
+                              int32_t *cls, double *t_wo, double *yaw, double *dims, int32_t *view_off,
+                              int64_t *frame_idx, float *box, uint8_t *mask, int64_t *n_present);
+
 /* How many objects can get a view-tiled cluster of `cluster` CTAs (2..4) with every CTA alone on its SM of `device`
  * (cudaOccupancyMaxActiveClusters; a cluster must fit one GPC, so this is less than SMs / cluster: 45 x 3 and 32 x 4
  * on a 148-SM B200).  The automatic launch configuration only picks a cluster size while the objects fit. */

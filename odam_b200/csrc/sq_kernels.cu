@@ -30,6 +30,7 @@
 #endif
 #include "sq_device.cuh"
 #include "sq_postproc.cuh"
+#include "sq_stage.h"
 
 namespace cg = cooperative_groups;
 

@@ -5,9 +5,10 @@ Same signature and return dict; the difference is structural.  The reference loo
 times (``load_pred_object`` per object per frame, one ``SuperQuadricOptimizer.run`` per object at 2.8 s each, one
 Qhull call per object); here
 
-  1. staging is vectorised over ALL track rows of ALL objects at once (`stage_tracks`): class, mean centre, chordal mean
-     of the per-frame yaws (closed form for rotations about z instead of scipy's ``Rotation.mean`` per object), mean dims,
-     and for every usable frame the detected box sides with the 20 px border rule -- straight into the packed C-ABI arrays;
+  1. staging is ONE native call over the rows of ALL objects (`stage_tracks` -> ``odam_sq_stage_tracks_host``): class,
+     mean centre, chordal mean of the per-frame yaws (closed form for rotations about z instead of scipy's
+     ``Rotation.mean`` per object), mean dims, and for every usable frame the detected box sides with the 20 px border
+     rule -- straight into the packed C-ABI arrays;
   2. every eligible object is optimised by ONE persistent kernel launch (``odam_sq_optimize_host``);
   3. ONE more launch, enqueued behind it inside the same call (``odam_sq_options.out_corners``), samples all final
      surfaces and computes their oriented boxes on the device (convex hull + min-area rectangle,
@@ -56,7 +57,31 @@ def stage_object(track, frame_ids, img_h, img_w):
 
 
 def stage_tracks(tracks, frame_ids, img_h, img_w):
-    """What run_multi_view.py:31-58 derives for every track, vectorised over all rows of all tracks.
+    """What run_multi_view.py:31-58 derives for every track, for all tracks in one native call
+    (``odam_sq_stage_tracks_host``, csrc/sq_stage.h: one pass over the rows, no CUDA).  Same dict as
+    `stage_tracks_numpy`, its vectorised numpy mirror."""
+    import ctypes as C
+    n = len(tracks)
+    L = _lib.load()
+    arrs = [np.ascontiguousarray(t, np.float64).reshape(-1, 82) for t in tracks]
+    rows_per = np.array([a.shape[0] for a in arrs], np.int64)
+    total = int(rows_per.sum())
+    fid = np.ascontiguousarray(frame_ids, np.int64).reshape(-1)
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+    cls, t_wo, yaw, dims = np.zeros(n, np.int32), np.zeros((n, 3)), np.zeros(n), np.zeros((n, 3))
+    view_off, n_present = np.zeros(n + 1, np.int32), np.zeros(n, np.int64)
+    frame_idx, box, mask = np.zeros(total, np.int64), np.zeros((total, 4), np.float32), np.zeros((total, 4), np.uint8)
+    _lib.check(L.odam_sq_stage_tracks_host(ptrs, _lib.ptr(rows_per), n, 82, _lib.ptr(fid), len(fid), int(img_h), int(img_w),
+                                           _lib.ptr(cls), _lib.ptr(t_wo), _lib.ptr(yaw), _lib.ptr(dims), _lib.ptr(view_off),
+                                           _lib.ptr(frame_idx), _lib.ptr(box), _lib.ptr(mask), _lib.ptr(n_present)))
+    sv = int(view_off[n])
+    return dict(cls=cls, t_wo=t_wo, yaw=yaw, dims=dims, view_off=view_off, frame_idx=frame_idx[:sv], box=box[:sv],
+                mask=mask[:sv], n_present=n_present)
+
+
+def stage_tracks_numpy(tracks, frame_ids, img_h, img_w):
+    """The numpy mirror of `stage_tracks` (kept for cross-checking the native entry), vectorised over all rows of all
+    tracks.
 
     Returns dict of arrays: cls [n] (int(median(class column)), tracking_gt_utils.py:153), t_wo [n,3] (mean centre over
     ALL rows, :155), yaw [n] (chordal mean of the yaws of the frames that are in `frame_ids`), dims [n,3] (mean over
@@ -160,7 +185,7 @@ def optim_process(tracks, img_names, T_wcs, P_cws, img_h, img_w, K, representati
         bad = st["cls"][(st["cls"] < 0) | (st["cls"] > 7)][0]
         raise KeyError(int(bad))                                # the reference's CLASS_MAPPER lookup fails the same way
     if run.size:
-        sel = np.concatenate([np.arange(st["view_off"][i], st["view_off"][i + 1]) for i in run])
+        sel = np.nonzero(np.repeat(views >= n_views, views))[0]        # the packed views of the eligible objects
         P32 = np.ascontiguousarray(np.asarray(P_cws, np.float64).reshape(-1, 12)[st["frame_idx"][sel]], np.float32)
         packed = api.PackedTracks(init=init[run], cls=st["cls"][run].astype(np.int32),
                                   view_off=np.concatenate([[0], np.cumsum(views[run])]).astype(np.int32),

@@ -245,3 +245,34 @@ def test_batched_staging_matches_reference_call_site():
     order = np.argsort(perm[a["frame_idx"]])
     assert np.array_equal(perm[a["frame_idx"]][order], b["frame_idx"]) and np.array_equal(a["box"][order], b["box"])
     assert stage_tracks([], G["img_names"], 968, 1296)["view_off"].tolist() == [0]
+
+
+def test_native_staging_matches_numpy_mirror_and_numpy_mean():
+    """odam_sq_stage_tracks_host (one native pass over the rows of all tracks) against its vectorised numpy mirror on
+    random ragged tracks -- frames outside frame_ids, duplicated frames, empty tracks, permuted frame ids, boxes across
+    the 20 px border -- and the mean centre against the reference's own expression np.mean(track[:, 9:12], axis=0)
+    (tracking_gt_utils.py:155), bit for bit."""
+    from odam_b200.run_multi_view import stage_tracks, stage_tracks_numpy
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        n, F = int(rng.integers(0, 12)), int(rng.integers(1, 40))
+        tracks = []
+        for i in range(n):
+            R = int(rng.integers(0 if i % 7 == 3 else 1, F + 5))
+            t = -np.ones((R, 82))
+            t[:, 0], t[:, 1] = rng.integers(-2, F + 3, R), rng.integers(0, 8, R)
+            x0, y0 = rng.uniform(-30, 1200, R), rng.uniform(-30, 900, R)
+            t[:, 2], t[:, 3], t[:, 4], t[:, 5] = x0, y0, x0 + rng.uniform(5, 400, R), y0 + rng.uniform(5, 300, R)
+            t[:, 6:9], t[:, 9:12], t[:, 12] = rng.uniform(0.2, 2, (R, 3)), rng.uniform(-3, 3, (R, 3)), rng.uniform(-4, 4, R)
+            tracks.append(t)
+        fid = rng.permutation(F + 2)[:F]
+        a, b = stage_tracks(tracks, fid, 968, 1296), stage_tracks_numpy(tracks, fid, 968, 1296)
+        full = np.array([len(t) > 0 for t in tracks], bool)
+        assert np.array_equal(a["cls"][full], b["cls"][full])
+        for k in ("view_off", "frame_idx", "box", "mask", "n_present"):
+            assert np.array_equal(a[k], b[k]), (trial, k)
+        for k in ("t_wo", "yaw", "dims"):
+            assert np.allclose(a[k], b[k], rtol=0, atol=1e-14), (trial, k)
+        for i, t in enumerate(tracks):
+            if len(t):
+                assert np.array_equal(a["t_wo"][i], np.mean(t[:, 9:12], axis=0))
