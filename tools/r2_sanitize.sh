@@ -17,6 +17,7 @@ tracks = api.pack_scene(synthetic.make_scene(3, 12, seed=3))
 for lay in (1, 2):
     api.optimize_host(tracks, prior=api.prior_table(), n_iters=3, threads=256, code_layout=lay)
 api.optimize_host(tracks, prior=api.prior_table(), n_iters=3, cluster=2)
+api.optimize_host(tracks, prior=api.prior_table(), n_iters=3, cluster=3, extras=("out_corners", "out_box_flag"))   # 128-register build, fused boxes
 print("ok", boxes.shape, cost.shape, flags.tolist())
 PY
 for tool in memcheck synccheck; do
