@@ -165,10 +165,10 @@ def map_reference_sampler():
     return None
 
 
-def cpu_baseline_config1(budget_s=40.0):
+def cpu_baseline_config1(budget_s=40.0, threads=None, max_objects=None):
     """SURVEY 8d / BASELINE configs[0]: 1 scene, 10 objects x 20 views, 200 iterations, prior on, as shipped (anomaly
-    mode on, sequential objects, torch's default intra-op threads).  Runs the whole config (about half a minute) unless
-    the budget runs out first; whole objects only."""
+    mode on, sequential objects, torch's default intra-op threads -- or `threads`).  Runs the whole config (about half
+    a minute) unless the budget or `max_objects` ends it first; whole objects only."""
     import torch
     from odam_b200 import api, synthetic
     from oracle import c_oracle
@@ -178,13 +178,15 @@ def cpu_baseline_config1(budget_s=40.0):
     scene = synthetic.make_scene(c["n_objects"], c["n_views"], seed=1)
     tracks = api.pack_scene(scene)
     prior = api.prior_table()
-    threads = torch.get_num_threads()
+    default_threads = torch.get_num_threads()
+    threads = threads or default_threads
     done, t_total = 0, 0.0
-    for i in range(scene.n):
+    for i in range(scene.n if max_objects is None else min(scene.n, max_objects)):
         t_total += cpu_port_worker(cpu_jobs(scene, tracks, prior, [i], c["n_iters"], threads)[0])
         done += 1
         if t_total > budget_s:
             break
+    torch.set_num_threads(default_threads)
     units = done * scene.V * c["n_iters"]
     return {"value": units / t_total, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"config 1 ({c['name']}, {c['n_iters']} iterations, prior on): {done} of {scene.n} objects, all "
@@ -463,6 +465,7 @@ def run_native(args):
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_config1(args.cpu_budget * 2.5)
         line["cpu_baseline_headline_config"] = cpu_baseline_sequential(scene, tracks, prior, args.cpu_budget)
+        line["cpu_baseline_1thread"] = cpu_baseline_config1(args.cpu_budget, threads=1, max_objects=3)   # 1 thread too
     emit(line)
     if world > 1:
         dist.destroy_process_group()
