@@ -339,7 +339,10 @@ __device__ __forceinline__ unsigned item_code(int item, int V, int slices)
 }
 
 // kCompact selects the small-instruction-footprint build (odam_sq_options::code_layout): same arithmetic either way.
-template <int kMaxThreads, bool kCompact, bool kSolo = false>
+// kProf: the instantiation that accumulates the per-phase cycle counts (odam_sq_options::out_cycles).  The marks are
+// compiled out of the production kernels: a predicate test, a branch and a volatile clock read at 15 places cost
+// 2.6 % (config 2) to 4.8 % (config 5) of the throughput even when no count is taken.
+template <int kMaxThreads, bool kCompact, bool kSolo = false, bool kProf = false>
 __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompact, kSolo)) sq_optimize_kernel(OptArgs A)
 {
     // fixed state in static shared memory (compile-time addresses), per-launch scratch in dynamic shared memory
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(kMaxThreads, SQ_MIN_BLOCKS(kMaxThreads, kCompa
 #endif
     const int tid = threadIdx.x, T = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
-    const bool prof = A.out_cycles != nullptr;
+    constexpr bool prof = kProf;
     // A cluster of C CTAs shares one object: every CTA runs the (cheap, deterministic) sampler redundantly and
     // projects its own tile of the views; the 13 partial sums meet through distributed shared memory once per iteration.
     const int C = A.cluster;
@@ -946,8 +949,14 @@ using OptKernel = void (*)(OptArgs);
 
 // every instantiation is capped at 64 registers/thread (1024 resident threads per SM worth of registers); the compact
 // layout only exists for CTAs of up to 256 threads (it is for many small CTAs per SM)
-static OptKernel pick_kernel(int threads, int compact, int solo = 0)
+static OptKernel pick_kernel(int threads, int compact, int solo = 0, int prof = 0)
 {
+    if (prof) {   // the same builds with the cycle marks compiled in
+        if (solo && !compact && threads <= 512) return sq_optimize_kernel<512, false, true, true>;
+        if (compact) return threads <= 256 ? sq_optimize_kernel<256, true, false, true> : nullptr;
+        return threads <= 256 ? sq_optimize_kernel<256, false, false, true>
+                              : (threads <= 512 ? sq_optimize_kernel<512, false, false, true> : sq_optimize_kernel<1024, false, false, true>);
+    }
     if (solo && !compact && threads <= 512) return sq_optimize_kernel<512, false, true>;   // one CTA per SM: 128 registers
     if (compact) return threads <= 256 ? sq_optimize_kernel<256, true> : nullptr;
     return threads <= 256 ? sq_optimize_kernel<256, false>
@@ -987,9 +996,11 @@ static int ensure_init(int device)
     }
     for (int compact = 0; compact < 2; compact++)
         for (int threads : {256, 512, 1024})
-            if (auto kern = pick_kernel(threads, compact))
-                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
-    CU(cudaFuncSetAttribute(pick_kernel(512, 0, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
+            for (int prof = 0; prof < 2; prof++)
+                if (auto kern = pick_kernel(threads, compact, 0, prof))
+                    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
+    for (int prof = 0; prof < 2; prof++)
+        CU(cudaFuncSetAttribute(pick_kernel(512, 0, 1, prof), cudaFuncAttributeMaxDynamicSharedMemorySize, D.max_smem_optin - (int)sizeof(Smem)));
     // How many view-tiled clusters can have every CTA on an SM of its own?  A cluster must fit one GPC, and the GPCs
     // of a 148-SM B200 do not hold a whole number of 3- or 4-CTA clusters: measured, 45 x 3 and 32 x 4 CTAs run one
     // per SM while 46 x 3 or 34 x 4 put two CTAs on some SMs and are 10..19 % slower than the next smaller cluster.
@@ -1117,7 +1128,7 @@ static int launch_optimize(DeviceState &D, const OptArgs &A0, const LaunchCfg &L
     A.red_offset = L.red_offset;
     A.stage_offset = L.stage_offset; A.stage_views = L.stage_views;
     if (A.out_status) CU(cudaMemsetAsync(A.out_status, 0, sizeof(int32_t) * A.n, st));  // CTAs OR their flags in
-    OptKernel kern = pick_kernel(L.threads, L.compact, L.solo);
+    OptKernel kern = pick_kernel(L.threads, L.compact, L.solo, A.out_cycles != nullptr);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
 #ifndef SQ_EXTRA_SMEM
